@@ -1,0 +1,76 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden/make_golden.py).
+
+The reference arithmetic is fp32 ATen; the oracle restates it with the same ops, so agreement is at
+fp32 round-off (matmul blocking may differ between host CPUs, hence 2e-5 rather than bit-exact on the
+MLP outputs; integer/sampler stages are compared exactly).
+"""
+import numpy as np
+import torch
+
+import pixel_nerf_yolo_b200.synth as synth
+from oracle import pixelnerf_oracle as O
+
+T = torch.from_numpy
+
+
+def _scene(num_objs):
+    s = synth.scene_config1(seed=5, num_views=3, C=512, size=128, feat=16, num_objs=num_objs)
+    return O.encode_cameras(s["latent"], s["poses"], s["focal"], s["image_wh"])
+
+
+def test_positional_encoding_matches_reference(golden):
+    out = O.positional_encoding(T(golden["pe_x"]))
+    assert torch.equal(out, T(golden["pe_out"]))
+
+
+def test_bilinear_index_matches_grid_sample(golden):
+    sc = _scene(1)
+    out = O.bilinear_index(sc.latent, T(golden["index_uv"]), sc.latent_scaling, sc.image_shape)
+    np.testing.assert_allclose(out.numpy(), golden["index_out"], atol=2e-6, rtol=0)
+    # the out-of-bounds (zero padding) branch is exercised
+    assert (golden["index_out"] == 0).all(axis=1).any()
+
+
+def test_resnetfc_matches_reference(golden):
+    out = O.resnetfc_forward(synth.mlp_state(21), T(golden["mlp_zx"]), 512, 5, 3, (3, 5))
+    np.testing.assert_allclose(out.reshape(2, 5, 4).numpy(), golden["mlp_out"], atol=2e-5, rtol=1e-5)
+
+
+def test_field_forward_matches_reference(golden):
+    sc = _scene(1)
+    for name, seed in (("field_coarse", 1), ("field_fine", 2)):
+        out = O.field_forward(sc, synth.mlp_state(seed), T(golden["field_xyz"]), T(golden["field_dirs"]))
+        np.testing.assert_allclose(out.numpy(), golden[name], atol=2e-5, rtol=1e-5)
+
+
+def _rays(golden, tag, num_objs):
+    allr = torch.cat([synth.target_rays(128, 15.0 + 20 * s, -10.0) for s in range(num_objs)])
+    return allr[:, T(golden[f"{tag}_ray_idx"]).long()]
+
+
+def _noise(golden, tag):
+    g = lambda k: T(golden[f"{tag}_noise_{k}"])
+    return O.RenderNoise(g("coarse"), g("fine_u"), g("fine_jitter"), g("depth"))
+
+
+def test_samplers_bit_exact(golden):
+    for tag, nobj in (("sb1", 1), ("sb2", 2)):
+        r = _rays(golden, tag, nobj).reshape(-1, 8)
+        n = _noise(golden, tag)
+        assert torch.equal(O.sample_coarse(r, n.coarse, 64), T(golden[f"{tag}_z_coarse"]))
+        w = T(golden[f"{tag}_coarse_weights"]).reshape(-1, 64)
+        assert torch.equal(O.sample_fine(r, w, n.fine_u, n.fine_jitter, 64), T(golden[f"{tag}_z_fine"]))
+        d = T(golden[f"{tag}_coarse_depth"]).reshape(-1)
+        assert torch.equal(O.sample_fine_depth(r, d, n.depth, 0.01), T(golden[f"{tag}_z_depth"]))
+
+
+def test_render_matches_reference(golden):
+    for tag, nobj in (("sb1", 1), ("sb2", 2)):
+        sc = _scene(nobj)
+        res = O.render(sc, synth.mlp_state(1), synth.mlp_state(2), _rays(golden, tag, nobj), _noise(golden, tag))
+        for lvl in ("coarse", "fine"):
+            for k in ("rgb", "depth", "weights"):
+                np.testing.assert_allclose(res[lvl][k].numpy(), golden[f"{tag}_{lvl}_{k}"], atol=3e-5, rtol=1e-4,
+                                           err_msg=f"{tag} {lvl} {k}")
+        # both passes have non-trivial opacity, so the MLP output really reaches the pixels
+        assert 0.3 < golden[f"{tag}_fine_weights"].sum(-1).mean() < 0.99
