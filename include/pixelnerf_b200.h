@@ -1,0 +1,160 @@
+/*
+ * pixelnerf_b200.h -- C ABI of the B200-native pixelNeRF-YOLO rendering hot path.
+ *
+ * The reference (kofinandi/pixel-nerf-yolo) is pure Python/PyTorch and has no FFI layer: the seam is
+ * its class API (NeRFRenderer.forward src/render/nerf.py:257-309, PixelNeRFNet.encode/forward
+ * src/model/models.py:92-318).  The drop-in Python classes in pixel-nerf-yolo_b200/ keep that API and
+ * call the entry points below through ctypes; INTEGRATION.md shows the binding.  Each entry point
+ * names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch caching allocator) unless noted;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*), no host sync;
+ *   - return value 0 = ok, negative = error; pnr_last_error() gives the thread-local message;
+ *   - no global state, re-entrant, callable from several host threads on different devices
+ *     (the reference's DataParallel runs one Python thread per GPU, src/render/nerf.py:373-377).
+ */
+#ifndef PIXELNERF_B200_H
+#define PIXELNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNR_ABI_VERSION 1
+
+/* precision of the field function (PixelNeRFNet.forward) */
+#define PNR_PREC_FP32 0 /* SIMT fp32 operands + fp32 accumulate: the <=1e-4 "accumulate-only" check build */
+#define PNR_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate in TMEM: the production path      */
+
+/* error codes */
+#define PNR_OK 0
+#define PNR_ERR_ARG (-1)      /* bad shape / null pointer / unsupported option            */
+#define PNR_ERR_CUDA (-2)     /* CUDA runtime error at enqueue time                        */
+#define PNR_ERR_UNSUPPORTED (-3) /* valid reference option that this build does not cover */
+
+/* State left behind by PixelNeRFNet.encode (src/model/models.py:92-151) plus the encoder output
+ * (SpatialEncoder.latent / latent_scaling, src/model/encoder.py:138-172), re-laid out for the GPU:
+ * feature maps are channels-last so one bilinear tap is one contiguous C-vector. */
+typedef struct pnr_scene {
+  const void* feat;    /* (SB*NS, Hl, Wl, C) channels-last; bf16 (feat_fp32=0) or fp32 (feat_fp32=1) */
+  const float* poses;  /* (SB*NS, 3, 4) world->camera [R^T | -R^T t]   models.py:116-118           */
+  const float* focal;  /* (SB*NS, 2) per view, fy already negated       models.py:126-137,225-227   */
+  const float* center; /* (SB*NS, 2) per view principal point           models.py:139-148,228-230   */
+  int32_t SB;          /* objects ("super batch")                                                   */
+  int32_t NS;          /* source views per object                                                   */
+  int32_t C;           /* latent channels (512 resnet34 x4 levels, 1792 YOLO backbone)              */
+  int32_t Hl, Wl;      /* feature-map size                                                          */
+  int32_t feat_fp32;   /* 0: bf16 maps, 1: fp32 maps                                                */
+  float image_w, image_h;          /* PixelNeRFNet.image_shape  models.py:122-123                   */
+  float lat_scale_x, lat_scale_y;  /* SpatialEncoder.latent_scaling  encoder.py:170-172             */
+} pnr_scene;
+
+/* Where the query points of a field evaluation come from. */
+typedef struct pnr_points {
+  const float* xyz;   /* mode 0: (SB, P, 3) world points   (PixelNeRFNet.forward argument)          */
+  const float* dirs;  /* mode 0: (SB, P, 3) view directions                                          */
+  const float* rays;  /* mode 1: (SB*B, 8) [o, d, near, far]; point (b,k) = o + z[b,k] d             */
+  const float* z;     /* mode 1: (SB*B, K) sample depths       (nerf.py:191,208-212)                 */
+  int32_t mode;       /* 0 explicit points, 1 rays x depths                                          */
+  int32_t P;          /* points per object (mode 1: B*K)                                             */
+  int32_t K;          /* mode 1: samples per ray                                                     */
+} pnr_points;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int pnr_version(void);
+const char* pnr_last_error(void);
+/* 1 if the current device is sm_100 (the only target this library has code for). */
+int pnr_device_supported(void);
+
+/* ---- ray tile: sampling / compositing / resampling (src/render/nerf.py) ------------------------- */
+/* sample_coarse, nerf.py:104-124.  steps = torch.linspace(0, 1-1/Kc, Kc) (passed in so that schedules
+ * with non power-of-two Kc stay bit-exact), noise (B,Kc) in [0,1).  z (B,Kc). */
+int pnr_sample_coarse(const float* rays, const float* steps, const float* noise, float* z,
+                      int B, int Kc, int lindisp, void* stream);
+
+/* composite, nerf.py:184-188 (deltas) + 229-255 (alpha, transmittance, weights, rgb, depth, white
+ * background).  rgb_sigma (B,K,4) = model output [r,g,b,sigma]; weights may be NULL. */
+int pnr_composite(const float* rgb_sigma, const float* z, const float* rays, float* weights,
+                  float* rgb, float* depth, int B, int K, int white_bkgd, void* stream);
+
+/* sample_fine (nerf.py:126-154) + sample_fine_depth (nerf.py:156-167) + cat/sort (nerf.py:300-301).
+ * weights (B,Kc) and depth (B) are the coarse composite outputs; u, jitter (B,Kf) and gauss (B,Kfd)
+ * the three noise draws.  z_out (B, Kc+Kf+Kfd) sorted ascending.  Optional debug outputs:
+ * inds_out (B,Kf) int32 searchsorted bins, z_fine_out (B,Kf), z_depth_out (B,Kfd) (may be NULL). */
+int pnr_sample_fine(const float* weights, const float* depth, const float* rays, const float* z_coarse,
+                    const float* u, const float* jitter, const float* gauss, float* z_out,
+                    int32_t* inds_out, float* z_fine_out, float* z_depth_out, int B, int Kc, int Kf,
+                    int Kfd, float depth_std, int lindisp, void* stream);
+
+/* ---- encode-side repack (SpatialEncoder.latent NCHW fp32 -> channels-last) ---------------------- */
+/* src (N, C, H, W) fp32 -> dst (N, H, W, C) bf16 (to_fp32=0) or fp32 (to_fp32=1). */
+int pnr_pack_features(const float* src, void* dst, int N, int C, int H, int W, int to_fp32, void* stream);
+
+/* ---- project + 4-tap gather + positional encoding, stand-alone ---------------------------------- */
+/* models.py:168-230 + encoder.py:79-108 + code.py:30-42.  For every (object, view, point) row
+ * r = (s*NS + v)*P + p writes latent_out[r, 0:C] (bf16 if out_fp32=0 else fp32) and zfeat_out[r, 0:42]
+ * fp32 = [PE(R x) (39), R d (3)].  Either output may be NULL. */
+int pnr_gather_encode(const pnr_scene* scene, const pnr_points* pts, void* latent_out, float* zfeat_out,
+                      int out_fp32, int num_freqs, float freq_factor, void* stream);
+
+/* PositionalEncoding.forward as a stand-alone operator (src/model/code.py:30-42):
+ * x (n, d) -> out (n, d * (2*num_freqs + include_input)) = [x, sin(f0 x), cos(f0 x), sin(f1 x), ...]. */
+int pnr_positional_encoding(const float* x, float* out, long long n, int d, int num_freqs,
+                            float freq_factor, int include_input, void* stream);
+
+/* SpatialEncoder.index as a stand-alone operator (src/model/encoder.py:79-108), bilinear,
+ * align_corners=True, zero padding.  uv (uv_views, P, 2) pixel coordinates with uv_views == 1 (broadcast)
+ * or SB*NS; out (SB*NS, C, P) fp32 in the reference's layout.  Only feat, SB, NS, C, Hl, Wl, feat_fp32,
+ * image_*, lat_scale_* of the scene are used. */
+int pnr_index_features(const pnr_scene* scene, const float* uv, int uv_views, int P, float* out, void* stream);
+
+/* ---- ResnetFC weights (src/model/resnetfc.py:103-132) ------------------------------------------- */
+/* fp32 parameters of one ResnetFC in state_dict order; all device pointers. */
+typedef struct pnr_mlp_params {
+  const float* lin_in_w;  const float* lin_in_b;     /* (H, d_in), (H)                 */
+  const float* lin_out_w; const float* lin_out_b;    /* (d_out, H), (d_out)            */
+  const float* fc0_w[8];  const float* fc0_b[8];     /* blocks.i.fc_0  (H,H),(H)       */
+  const float* fc1_w[8];  const float* fc1_b[8];     /* blocks.i.fc_1  (H,H),(H)       */
+  const float* linz_w[8]; const float* linz_b[8];    /* lin_z.i  (H, d_latent),(H)     */
+  int32_t d_in, d_latent, d_hidden, d_out, n_blocks, combine_layer;
+} pnr_mlp_params;
+
+/* Bytes of the packed bf16 weight stream + fp32 bias tables for the tcgen05 path. */
+size_t pnr_mlp_pack_bytes(const pnr_mlp_params* p);
+/* Build the packed blob (device, caller-allocated, 1024-byte aligned) from fp32 parameters.
+ * A derived cache: rebuilt after load_state_dict / optimizer steps, never saved. */
+int pnr_mlp_pack(const pnr_mlp_params* p, void* packed, void* stream);
+
+/* ---- field function: PixelNeRFNet.forward (src/model/models.py:153-318) -------------------------- */
+/* out (SB*P, 4) fp32 = [sigmoid(rgb), relu(sigma)].  precision PNR_PREC_FP32 uses `params` and a
+ * caller workspace of pnr_field_workspace_bytes(); PNR_PREC_BF16 uses `packed` (from pnr_mlp_pack)
+ * and needs no workspace. */
+size_t pnr_field_workspace_bytes(const pnr_scene* scene, const pnr_points* pts, int precision);
+int pnr_field_forward(const pnr_scene* scene, const pnr_points* pts, const pnr_mlp_params* params,
+                      const void* packed, float* out, void* workspace, size_t workspace_bytes,
+                      int precision, int num_freqs, float freq_factor, void* stream);
+
+/* ResnetFC.forward as a stand-alone operator (src/model/resnetfc.py:134-186), fp32 arithmetic.
+ * zx (rows, d_latent + d_in) fp32, rows ordered (object, view, point) with NS views and P points per
+ * object (combine_inner_dims = (NS, P)); out (rows / NS, d_out) raw lin_out values. */
+size_t pnr_resnetfc_workspace_bytes(const pnr_mlp_params* p, long long rows);
+int pnr_resnetfc_forward(const pnr_mlp_params* p, const float* zx, long long rows, int NS, int P,
+                         float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the last pnr_* call on this thread launched (for bench.py's gpu_launches). */
+int pnr_last_launch_count(void);
+
+/* tcgen05 building-block self test: D(128 x N) = A(128 x K) * B(N x K)^T with bf16 operands staged
+ * exactly like the fused kernel (bulk-copied pre-swizzled A, thread-written swizzled B, TMEM
+ * accumulator, tcgen05.ld epilogue).  a (128,K), b (N,K) fp32 device inputs, d (128,N) fp32 device
+ * output; workspace: K/64 * 16 KiB, 1024-byte aligned.  N in {16,32,48,64}, K multiple of 64 <= 512. */
+int pnr_umma_selftest(const float* a, const float* b, float* d, void* workspace, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELNERF_B200_H */

@@ -1,0 +1,136 @@
+"""ctypes binding of the C-ABI library (include/pixelnerf_b200.h).
+
+The library is built in-tree (``python -m pixel_nerf_yolo_b200.build`` or ``__graft_entry__.build()``)
+as ``pixel-nerf-yolo_b200/csrc/libpixelnerf_b200.so``.  If it is missing, or the device is not sm_100,
+every entry point raises: there is no CPU or eager-PyTorch fallback on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpixelnerf_b200.so")
+
+PREC_FP32 = 0
+PREC_BF16 = 1
+
+# every symbol include/pixelnerf_b200.h declares
+EXPORTS = [
+    "pnr_version", "pnr_last_error", "pnr_device_supported", "pnr_sample_coarse", "pnr_composite",
+    "pnr_sample_fine", "pnr_pack_features", "pnr_gather_encode", "pnr_mlp_pack_bytes", "pnr_mlp_pack",
+    "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_umma_selftest",
+    "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
+]
+
+
+class Scene(C.Structure):
+    _fields_ = [("feat", C.c_void_p), ("poses", C.c_void_p), ("focal", C.c_void_p), ("center", C.c_void_p),
+                ("SB", C.c_int32), ("NS", C.c_int32), ("C", C.c_int32), ("Hl", C.c_int32), ("Wl", C.c_int32),
+                ("feat_fp32", C.c_int32), ("image_w", C.c_float), ("image_h", C.c_float),
+                ("lat_scale_x", C.c_float), ("lat_scale_y", C.c_float)]
+
+
+class Points(C.Structure):
+    _fields_ = [("xyz", C.c_void_p), ("dirs", C.c_void_p), ("rays", C.c_void_p), ("z", C.c_void_p),
+                ("mode", C.c_int32), ("P", C.c_int32), ("K", C.c_int32)]
+
+
+class MlpParams(C.Structure):
+    _fields_ = [("lin_in_w", C.c_void_p), ("lin_in_b", C.c_void_p), ("lin_out_w", C.c_void_p),
+                ("lin_out_b", C.c_void_p), ("fc0_w", C.c_void_p * 8), ("fc0_b", C.c_void_p * 8),
+                ("fc1_w", C.c_void_p * 8), ("fc1_b", C.c_void_p * 8), ("linz_w", C.c_void_p * 8),
+                ("linz_b", C.c_void_p * 8), ("d_in", C.c_int32), ("d_latent", C.c_int32),
+                ("d_hidden", C.c_int32), ("d_out", C.c_int32), ("n_blocks", C.c_int32),
+                ("combine_layer", C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the library.  Raises NativeLibraryError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). This package has no CPU / eager-PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    lib.pnr_version.restype = i32
+    lib.pnr_last_error.restype = C.c_char_p
+    lib.pnr_device_supported.restype = i32
+    lib.pnr_last_launch_count.restype = i32
+    lib.pnr_sample_coarse.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.pnr_composite.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.pnr_sample_fine.argtypes = [vp] * 11 + [i32, i32, i32, i32, f32, i32, vp]
+    lib.pnr_pack_features.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.pnr_gather_encode.argtypes = [C.POINTER(Scene), C.POINTER(Points), vp, vp, i32, i32, f32, vp]
+    lib.pnr_mlp_pack_bytes.argtypes = [C.POINTER(MlpParams)]
+    lib.pnr_mlp_pack_bytes.restype = C.c_size_t
+    lib.pnr_mlp_pack.argtypes = [C.POINTER(MlpParams), vp, vp]
+    lib.pnr_field_workspace_bytes.argtypes = [C.POINTER(Scene), C.POINTER(Points), i32]
+    lib.pnr_field_workspace_bytes.restype = C.c_size_t
+    lib.pnr_field_forward.argtypes = [C.POINTER(Scene), C.POINTER(Points), C.POINTER(MlpParams), vp, vp, vp,
+                                      C.c_size_t, i32, i32, f32, vp]
+    lib.pnr_umma_selftest.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    lib.pnr_resnetfc_workspace_bytes.argtypes = [C.POINTER(MlpParams), C.c_longlong]
+    lib.pnr_resnetfc_workspace_bytes.restype = C.c_size_t
+    lib.pnr_resnetfc_forward.argtypes = [C.POINTER(MlpParams), vp, C.c_longlong, i32, i32, vp, vp, C.c_size_t, vp]
+    lib.pnr_positional_encoding.argtypes = [vp, vp, C.c_longlong, i32, i32, f32, i32, vp]
+    lib.pnr_index_features.argtypes = [C.POINTER(Scene), vp, i32, i32, vp, vp]
+    for name in EXPORTS:
+        getattr(lib, name)          # AttributeError here = header and library disagree
+    if lib.pnr_version() != 1:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.pnr_version()}, binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pnr_last_error().decode()
+        if rc == -3:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: the pixelnerf_b200 path runs on sm_100 GPUs only (no CPU fallback)")
+
+
+_device_checked = set()
+
+
+def require_device(device: torch.device) -> None:
+    """Fail loudly on anything that is not a B200-class (sm_100) device."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _device_checked:
+        return
+    with torch.cuda.device(idx):
+        if not load().pnr_device_supported():
+            raise RuntimeError("pixelnerf_b200: " + load().pnr_last_error().decode())
+    _device_checked.add(idx)
+
+
+def last_launch_count() -> int:
+    return load().pnr_last_launch_count()

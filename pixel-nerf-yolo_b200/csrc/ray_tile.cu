@@ -1,0 +1,244 @@
+// F1: per-ray sampling, alpha compositing and inverse-CDF resampling (src/render/nerf.py).
+// One warp owns one ray; the K-length recurrences (transmittance product, CDF sum) are warp-level
+// prefix scans carried across 32-sample chunks.  Scans run in double and round to float per element,
+// which is what torch.cumsum / torch.cumprod do on the CPU oracle (acc_type<float> = double).
+#include "pnr_common.cuh"
+
+namespace pnr {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxSortN = 512;   // padded (power of two) sort buffer per warp
+
+__device__ __forceinline__ float lerp_depth(float near, float far, float s, int lindisp) {
+  if (!lindisp)   // near * (1 - s) + far * s          nerf.py:119,151 (separately rounded)
+    return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, s)), __fmul_rn(far, s));
+  // 1 / (1/near * (1 - s) + 1/far * s)                nerf.py:121,153
+  float a = __fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, s));
+  float b = __fmul_rn(__fdiv_rn(1.0f, far), s);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+
+__global__ void sample_coarse_kernel(const float* __restrict__ rays, const float* __restrict__ steps,
+                                     const float* __restrict__ noise, float* __restrict__ z, int B, int Kc,
+                                     float step, int lindisp) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Kc) return;
+  int b = (int)(i / Kc), k = (int)(i - (long long)b * Kc);
+  float near = rays[b * 8 + 6], far = rays[b * 8 + 7];
+  float s = __fadd_rn(steps[k], __fmul_rn(noise[i], step));   // z_steps += rand * step   nerf.py:117
+  z[i] = lerp_depth(near, far, s, lindisp);
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan_mul(T v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v *= o;
+  }
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan_add(T v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// nerf.py:184-188 + 229-255
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_kernel(const float4* __restrict__ rgb_sigma, const float* __restrict__ z,
+                 const float* __restrict__ rays, float* __restrict__ weights, float* __restrict__ rgb,
+                 float* __restrict__ depth, int B, int K, int white_bkgd) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float far = rays[b * 8 + 7];
+  const float* zr = z + (size_t)b * K;
+  const float4* o = rgb_sigma + (size_t)b * K;
+  double carry = 1.0;                      // running product of (1 - alpha + 1e-10), exclusive
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_w = 0.f;
+  for (int base = 0; base < K; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < K;
+    float zi = 0.f, alpha = 0.f;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      zi = zr[i];
+      float znext = (i + 1 < K) ? zr[i + 1] : far;          // delta_inf = far - z_last   nerf.py:187
+      float delta = __fsub_rn(znext, zi);
+      c = o[i];
+      float sig = fmaxf(c.w, 0.0f);
+      alpha = __fsub_rn(1.0f, expf(__fmul_rn(-delta, sig))); // 1 - exp(-delta * relu(sigma))
+    }
+    float a_shift = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+    double incl = warp_incl_scan_mul<double>((double)a_shift, lane);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0;
+    float T = (float)(carry * excl);       // cumprod([1, a_0, a_1, ...])[i], rounded per element
+    carry = carry * __shfl_sync(0xffffffffu, incl, 31);
+    float w = __fmul_rn(alpha, T);
+    if (valid) {
+      if (weights) weights[(size_t)b * K + i] = w;
+      acc_r += w * c.x; acc_g += w * c.y; acc_b += w * c.z;
+      acc_d += w * zi;  acc_w += w;
+    }
+  }
+  acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b);
+  acc_d = warp_sum(acc_d); acc_w = warp_sum(acc_w);
+  if (lane == 0) {
+    if (white_bkgd) {                      // rgb + 1 - pix_alpha                        nerf.py:247-250
+      acc_r = __fsub_rn(__fadd_rn(acc_r, 1.0f), acc_w);
+      acc_g = __fsub_rn(__fadd_rn(acc_g, 1.0f), acc_w);
+      acc_b = __fsub_rn(__fadd_rn(acc_b, 1.0f), acc_w);
+    }
+    rgb[b * 3 + 0] = acc_r; rgb[b * 3 + 1] = acc_g; rgb[b * 3 + 2] = acc_b;
+    depth[b] = acc_d;
+  }
+}
+
+// In-warp bitonic sort of n (power of two, <= kMaxSortN) floats in shared memory, ascending.
+__device__ __forceinline__ void warp_bitonic_sort(float* s, int n, int lane) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < n / 2; t += 32) {
+        // t-th compare-exchange pair of this stage
+        int i = 2 * t - (t & (j - 1));
+        int p = i + j;
+        bool up = ((i & k) == 0);
+        float a = s[i], c = s[p];
+        if ((a > c) == up) { s[i] = c; s[p] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// nerf.py:126-167 + 300-301
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_fine_kernel(const float* __restrict__ weights, const float* __restrict__ depth,
+                   const float* __restrict__ rays, const float* __restrict__ z_coarse,
+                   const float* __restrict__ u, const float* __restrict__ jitter,
+                   const float* __restrict__ gauss, float* __restrict__ z_out, int32_t* __restrict__ inds_out,
+                   float* __restrict__ z_fine_out, float* __restrict__ z_depth_out, int B, int Kc, int Kf,
+                   int Kfd, float depth_std, int lindisp, int n_pad) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * kWarpsPerBlock + wid;
+  if (b >= B) return;
+  float* cdf = smem + (size_t)wid * (2 * kMaxSortN);       // Kc+1 entries
+  float* srt = cdf + kMaxSortN;                            // n_pad entries
+  const float near = rays[b * 8 + 6], far = rays[b * 8 + 7];
+  const int Ktot = Kc + Kf + Kfd;
+
+  if (Kf > 0) {
+    const float* w = weights + (size_t)b * Kc;
+    // pdf = (w + 1e-5) / sum(w + 1e-5)                    nerf.py:136-137
+    float part = 0.f;
+    for (int i = lane; i < Kc; i += 32) part += __fadd_rn(w[i], 1e-5f);
+    const float tot = warp_sum(part);
+    // cdf = [0, cumsum(pdf)] : double running sum, rounded to float per element  nerf.py:138-139
+    double carry = 0.0;
+    if (lane == 0) cdf[0] = 0.0f;
+    for (int base = 0; base < Kc; base += 32) {
+      int i = base + lane;
+      float pdf = (i < Kc) ? __fdiv_rn(__fadd_rn(w[i], 1e-5f), tot) : 0.0f;
+      double incl = warp_incl_scan_add<double>((double)pdf, lane);
+      if (i < Kc) cdf[i + 1] = (float)(carry + incl);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    for (int j = lane; j < Kf; j += 32) {
+      float uj = u[(size_t)b * Kf + j];
+      // searchsorted(cdf, u, right=True): first index with cdf[idx] > u   nerf.py:144
+      int lo = 0, hi = Kc + 1;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= uj) lo = mid + 1; else hi = mid;
+      }
+      float ind = fmaxf((float)lo - 1.0f, 0.0f);           // clamp_min(inds - 1, 0)       nerf.py:144-145
+      float s = __fdiv_rn(__fadd_rn(ind, jitter[(size_t)b * Kf + j]), (float)Kc);   // nerf.py:147
+      float zz = lerp_depth(near, far, s, lindisp);
+      srt[Kc + j] = zz;
+      if (inds_out) inds_out[(size_t)b * Kf + j] = (int32_t)ind;
+      if (z_fine_out) z_fine_out[(size_t)b * Kf + j] = zz;
+    }
+  }
+  if (Kfd > 0) {
+    const float d = depth[b];
+    for (int j = lane; j < Kfd; j += 32) {
+      // depth + randn * depth_std, clamped to [near, far]   nerf.py:163-166
+      float zz = __fadd_rn(d, __fmul_rn(gauss[(size_t)b * Kfd + j], depth_std));
+      zz = fmaxf(fminf(zz, far), near);
+      srt[Kc + Kf + j] = zz;
+      if (z_depth_out) z_depth_out[(size_t)b * Kfd + j] = zz;
+    }
+  }
+  for (int i = lane; i < Kc; i += 32) srt[i] = z_coarse[(size_t)b * Kc + i];
+  for (int i = Ktot + lane; i < n_pad; i += 32) srt[i] = __int_as_float(0x7f800000);   // +inf padding
+  __syncwarp();
+  warp_bitonic_sort(srt, n_pad, lane);                     // torch.sort(cat(...))   nerf.py:300-301
+  for (int i = lane; i < Ktot; i += 32) z_out[(size_t)b * Ktot + i] = srt[i];
+}
+
+}  // namespace pnr
+
+using namespace pnr;
+
+extern "C" int pnr_sample_coarse(const float* rays, const float* steps, const float* noise, float* z, int B,
+                                 int Kc, int lindisp, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(rays && steps && noise && z, PNR_ERR_ARG, "pnr_sample_coarse: null pointer");
+  PNR_REQUIRE(B >= 0 && Kc > 0, PNR_ERR_ARG, "pnr_sample_coarse: bad shape B=%d Kc=%d", B, Kc);
+  if (B == 0) return PNR_OK;
+  long long n = (long long)B * Kc;
+  float step = (float)(1.0 / (double)Kc);
+  sample_coarse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays, steps, noise, z, B,
+                                                                                      Kc, step, lindisp);
+  PNR_CHECK_LAUNCH("sample_coarse_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_composite(const float* rgb_sigma, const float* z, const float* rays, float* weights,
+                             float* rgb, float* depth, int B, int K, int white_bkgd, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(rgb_sigma && z && rays && rgb && depth, PNR_ERR_ARG, "pnr_composite: null pointer");
+  PNR_REQUIRE(B >= 0 && K > 0, PNR_ERR_ARG, "pnr_composite: bad shape B=%d K=%d", B, K);
+  if (B == 0) return PNR_OK;
+  composite_kernel<<<(B + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      (const float4*)rgb_sigma, z, rays, weights, rgb, depth, B, K, white_bkgd);
+  PNR_CHECK_LAUNCH("composite_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_sample_fine(const float* weights, const float* depth, const float* rays,
+                               const float* z_coarse, const float* u, const float* jitter, const float* gauss,
+                               float* z_out, int32_t* inds_out, float* z_fine_out, float* z_depth_out, int B,
+                               int Kc, int Kf, int Kfd, float depth_std, int lindisp, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(rays && z_coarse && z_out, PNR_ERR_ARG, "pnr_sample_fine: null pointer");
+  PNR_REQUIRE(Kf == 0 || (weights && u && jitter), PNR_ERR_ARG, "pnr_sample_fine: importance inputs missing");
+  PNR_REQUIRE(Kfd == 0 || (depth && gauss), PNR_ERR_ARG, "pnr_sample_fine: depth-sample inputs missing");
+  PNR_REQUIRE(B >= 0 && Kc > 0 && Kf >= 0 && Kfd >= 0, PNR_ERR_ARG, "pnr_sample_fine: bad shape");
+  int Ktot = Kc + Kf + Kfd;
+  int n_pad = 32;
+  while (n_pad < Ktot) n_pad <<= 1;
+  PNR_REQUIRE(n_pad <= kMaxSortN && Kc + 1 <= kMaxSortN, PNR_ERR_UNSUPPORTED,
+              "pnr_sample_fine: %d samples per ray exceeds the %d-sample tile", Ktot, kMaxSortN);
+  if (B == 0) return PNR_OK;
+  size_t smem = (size_t)kWarpsPerBlock * 2 * kMaxSortN * sizeof(float);
+  sample_fine_kernel<<<(B + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, smem,
+                       (cudaStream_t)stream>>>(weights, depth, rays, z_coarse, u, jitter, gauss, z_out, inds_out,
+                                               z_fine_out, z_depth_out, B, Kc, Kf, Kfd, depth_std, lindisp, n_pad);
+  PNR_CHECK_LAUNCH("sample_fine_kernel");
+  return PNR_OK;
+}

@@ -1,0 +1,144 @@
+"""Multi-GPU rendering: rays shard, nothing else moves.
+
+The reference's only multi-GPU mechanism is ``torch.nn.DataParallel(dim=1)`` (src/render/nerf.py:373-377),
+which re-broadcasts every parameter and the encoded feature maps to every GPU on EVERY call and gathers
+on GPU 0.  Rays are independent, so here:
+
+* weights and the encoded scene are replicated once (each rank encodes / packs for itself);
+* the ray batch is split into contiguous, tile-aligned slices (``shard_bounds``), one per rank;
+* the per-ray outputs (rgb, depth[, weights]) are gathered ONCE per call with one NCCL all-gather
+  (``ShardedRenderer``, one process per GPU under torchrun), or with peer copies to the first device
+  (``MultiDeviceRenderer``, the single-process equivalent behind ``bind_parallel(net, gpus)``).
+
+Noise is drawn for the FULL batch and sliced, so an N-GPU render is bit-identical to the 1-GPU render.
+The host logic (bounds, padding, gather) is device-agnostic and is tested on CPU with the gloo backend.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+RAY_TILE = 32      # slices are aligned to a multiple of this many rays
+
+
+def shard_bounds(n: int, world: int, tile: int = RAY_TILE) -> List[Tuple[int, int]]:
+    """Contiguous [start, end) slice of ``n`` rays for each of ``world`` ranks, sizes differing by at most
+    one tile, every boundary (except the last) a multiple of ``tile``."""
+    tiles = (n + tile - 1) // tile
+    base, extra = divmod(tiles, world)
+    out, start = [], 0
+    for r in range(world):
+        cnt = (base + (1 if r < extra else 0)) * tile
+        end = min(n, start + cnt)
+        out.append((start, end))
+        start = end
+    return out
+
+
+def _pad_rows(t: torch.Tensor, rows: int) -> torch.Tensor:
+    if t.shape[0] == rows:
+        return t.contiguous()
+    pad = torch.zeros((rows - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    return torch.cat((t, pad), dim=0)
+
+
+def all_gather_rows(local: torch.Tensor, bounds: Sequence[Tuple[int, int]], group=None) -> torch.Tensor:
+    """All-gather row slices of unequal length: one collective on a padded buffer, then trim."""
+    world = len(bounds)
+    longest = max(e - s for s, e in bounds)
+    buf = _pad_rows(local, longest)
+    out = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device=buf.device)
+    if buf.is_cuda:
+        dist.all_gather_into_tensor(out, buf, group=group)      # one NCCL all-gather over NVLink
+    else:
+        dist.all_gather(list(out.unbind(0)), buf, group=group)  # gloo (CPU tests of the host logic)
+    return torch.cat([out[r, : e - s] for r, (s, e) in enumerate(bounds)], dim=0)
+
+
+def slice_noise(noise: Optional[Dict[str, torch.Tensor]], sb: int, b_total: int, s: int, e: int):
+    """Noise tensors are (SB*B, k); take rays [s, e) of every object."""
+    if noise is None:
+        return None
+    out = {}
+    for k, v in noise.items():
+        out[k] = None if v is None else v.reshape(sb, b_total, v.shape[-1])[:, s:e].reshape(sb * (e - s), v.shape[-1]).contiguous()
+    return out
+
+
+class ShardedRenderer(torch.nn.Module):
+    """One process per GPU (torchrun).  ``render_fn(rays_slice, noise_slice) -> (rgb (SB,b,3), depth (SB,b))``
+    is the local single-GPU render; every rank receives the full (SB, B, 3)/(SB, B) result."""
+
+    def __init__(self, render_fn: Callable, group=None, tile: int = RAY_TILE):
+        super().__init__()
+        self.render_fn = render_fn
+        self.group = group
+        self.tile = tile
+
+    def forward(self, rays: torch.Tensor, noise: Optional[Dict[str, torch.Tensor]] = None):
+        world = dist.get_world_size(self.group)
+        rank = dist.get_rank(self.group)
+        sb, b_total = rays.shape[0], rays.shape[1]
+        bounds = shard_bounds(b_total, world, self.tile)
+        s, e = bounds[rank]
+        if e > s:
+            rgb, depth = self.render_fn(rays[:, s:e].contiguous(), slice_noise(noise, sb, b_total, s, e))
+        else:   # more ranks than ray tiles: this rank only takes part in the gather
+            rgb, depth = rays.new_zeros(sb, 0, 3), rays.new_zeros(sb, 0)
+        # pack (r, g, b, depth) = 16 B/ray, ray-major, and gather once
+        packed = torch.cat((rgb, depth.unsqueeze(-1)), dim=-1).permute(1, 0, 2).contiguous()      # (b, SB, 4)
+        full = all_gather_rows(packed, bounds, self.group).permute(1, 0, 2)                        # (SB, B, 4)
+        return full[..., :3].contiguous(), full[..., 3].contiguous()
+
+
+class MultiDeviceRenderer(torch.nn.Module):
+    """Single-process multi-device driver behind ``NeRFRenderer.bind_parallel(net, gpus)``: the wrapped
+    ``_RenderWrapper`` is replicated to every device once; its encoded scene and parameters are re-copied
+    only when they changed (new ``encode`` / optimizer step); each call launches one ray slice per device
+    asynchronously and gathers the outputs on the first device with peer copies over NVLink."""
+
+    def __init__(self, wrapped, gpus: Sequence[int]):
+        super().__init__()
+        self.module = wrapped
+        self.devices = [torch.device("cuda", int(g)) for g in gpus]
+        self._replicas = None
+        self._key = None
+
+    def _state_key(self):
+        net = self.module.net
+        return (tuple((p.data_ptr(), p._version) for p in net.parameters()), net.encoder.latent.data_ptr(),
+                net.encoder.latent._version, net.poses.data_ptr(), net.poses._version)
+
+    def _sync(self):
+        key = self._state_key()
+        if self._replicas is not None and key == self._key:
+            return
+        src = self.module.net
+        reps = [self.module]
+        for d in self.devices[1:]:
+            with torch.cuda.device(d):
+                r = copy.deepcopy(self.module).to(d)
+                r.net.encoder.set_latent(src.encoder.latent.to(d))
+                r.net.num_objs, r.net.num_views_per_obj = src.num_objs, src.num_views_per_obj
+                r.net._cam_cache = None
+            reps.append(r)
+        self._replicas, self._key = reps, key
+
+    def forward(self, rays, want_weights=False):
+        self._sync()
+        sb, b_total = rays.shape[0], rays.shape[1]
+        bounds = shard_bounds(b_total, len(self.devices))
+        outs = []
+        for rep, d, (s, e) in zip(self._replicas, self.devices, bounds):
+            with torch.cuda.device(d):
+                outs.append(rep(rays[:, s:e].to(d, non_blocking=True), want_weights=want_weights))
+        d0 = self.devices[0]
+        if isinstance(outs[0], tuple):
+            return tuple(torch.cat([o[i].to(d0, non_blocking=True) for o in outs], dim=1) for i in range(2))
+        merged: Dict = {}
+        for lvl in outs[0]:
+            merged[lvl] = {k: torch.cat([o[lvl][k].to(d0, non_blocking=True) for o in outs], dim=1) for k in outs[0][lvl]}
+        return merged

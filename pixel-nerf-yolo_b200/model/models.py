@@ -1,0 +1,252 @@
+"""PixelNeRFNet: drop-in for ``src/model/models.py`` whose ``forward`` is one fused sm_100a kernel.
+
+``encode`` keeps the reference's bookkeeping (world->camera poses, focal sign flip, principal point,
+``image_shape``; models.py:92-151) and runs the encoder trunk in PyTorch; ``forward`` hands
+(points, view directions, scene) to ``pnr_field_forward`` which does projection, the 4-tap gather,
+positional encoding, the ResnetFC with the view mean and the output activations (models.py:153-318).
+"""
+import os
+import os.path as osp
+import warnings
+
+import torch
+
+from .. import _lib
+from .code import PositionalEncoding
+from .model_util import make_encoder, make_mlp
+
+
+class PixelNeRFNet(torch.nn.Module):
+    def __init__(self, conf, stop_encoder_grad=False):
+        super().__init__()
+        self.encoder = make_encoder(conf["encoder"])
+        self.use_encoder = conf.get_bool("use_encoder", True)
+        self.use_xyz = conf.get_bool("use_xyz", False)
+        assert self.use_encoder or self.use_xyz
+        self.normalize_z = conf.get_bool("normalize_z", True)
+        self.stop_encoder_grad = stop_encoder_grad
+        self.use_code = conf.get_bool("use_code", False)
+        self.use_code_viewdirs = conf.get_bool("use_code_viewdirs", True)
+        self.use_viewdirs = conf.get_bool("use_viewdirs", False)
+        self.use_global_encoder = conf.get_bool("use_global_encoder", False)
+        # The fused kernels implement the switch set of every shipped conf (conf/default*.conf, conf/exp/*.conf).
+        unsupported = []
+        if not self.use_encoder: unsupported.append("use_encoder=False")
+        if not self.use_xyz: unsupported.append("use_xyz=False")
+        if not self.normalize_z: unsupported.append("normalize_z=False")
+        if not self.use_code: unsupported.append("use_code=False")
+        if self.use_code_viewdirs: unsupported.append("use_code_viewdirs=True")
+        if not self.use_viewdirs: unsupported.append("use_viewdirs=False")
+        if self.use_global_encoder: unsupported.append("use_global_encoder=True")
+        if unsupported:
+            raise NotImplementedError("PixelNeRFNet (B200 path) does not build: " + ", ".join(unsupported))
+
+        d_latent = self.encoder.latent_size
+        self.code = PositionalEncoding.from_conf(conf["code"], d_in=3)
+        if not self.code.include_input:
+            raise NotImplementedError("PixelNeRFNet (B200 path): code.include_input=False is not built")
+        d_in = self.code.d_out + 3            # PE(xyz) ++ raw view directions (models.py:47-59)
+        self.latent_size = self.encoder.latent_size
+        self.mlp_coarse = make_mlp(conf["mlp_coarse"], d_in, d_latent)
+        self.mlp_fine = make_mlp(conf["mlp_fine"], d_in, d_latent, allow_empty=True)
+        self.register_buffer("poses", torch.empty(1, 3, 4), persistent=False)
+        self.register_buffer("image_shape", torch.empty(2), persistent=False)
+        self.yolo = conf.get_bool("mlp_coarse.yolo", False)
+        if self.yolo:
+            raise NotImplementedError("PixelNeRFNet (B200 path): the YOLO head (mlp_coarse.yolo) is the next row "
+                                      "after the NeRF path (SURVEY.md section 8f) and is not built yet")
+        self.d_in = d_in
+        self.d_out = conf.get_int("mlp_coarse.d_out", 4)
+        if self.d_out != 4:
+            raise NotImplementedError("PixelNeRFNet (B200 path): d_out must be 4 (rgb + sigma)")
+        self.d_latent = d_latent
+        self.register_buffer("focal", torch.empty(1, 2), persistent=False)
+        self.register_buffer("c", torch.empty(1, 2), persistent=False)
+        self.num_objs = 0
+        self.num_views_per_obj = 1
+        # "bf16": tcgen05 tensor-core path (production).  "fp32": SIMT fp32 check path.
+        self.precision = "bf16"
+        self.fp32_chunk_points = 50000
+        self._cam_cache = None
+
+    # ------------------------------------------------------------------------------------------------
+    def encode(self, images, poses, focal, z_bounds=None, c=None):
+        """images (SB, NS, 3, H, W) or (NS, 3, H, W); poses camera-to-world (.., 4, 4); focal / c in any of
+        the reference's formats (models.py:92-151)."""
+        self.num_objs = images.size(0)
+        if len(images.shape) == 5:
+            assert len(poses.shape) == 4
+            assert poses.size(1) == images.size(1)
+            self.num_views_per_obj = images.size(1)
+            images = images.reshape(-1, *images.shape[2:])
+            poses = poses.reshape(-1, 4, 4)
+        else:
+            self.num_views_per_obj = 1
+        self.encoder(images)
+        self.set_cameras(poses, focal, (images.shape[-1], images.shape[-2]), c)
+
+    def set_cameras(self, poses, focal, image_wh, c=None):
+        """The camera half of ``encode`` (models.py:116-148) without running the encoder trunk."""
+        rot = poses[:, :3, :3].transpose(1, 2)
+        trans = -torch.bmm(rot, poses[:, :3, 3:])
+        self.poses = torch.cat((rot, trans), dim=-1).float()
+        self.image_shape[0] = image_wh[0]
+        self.image_shape[1] = image_wh[1]
+        if len(focal.shape) == 0:
+            focal = focal[None, None].repeat((1, 2))
+        elif len(focal.shape) == 1:
+            focal = focal.unsqueeze(-1).repeat((1, 2))
+        else:
+            focal = focal.clone()
+        self.focal = focal.float().to(self.poses.device)
+        self.focal[..., 1] *= -1.0
+        if c is None:
+            c = (self.image_shape * 0.5).unsqueeze(0)
+        elif len(c.shape) == 0:
+            c = c[None, None].repeat((1, 2))
+        elif len(c.shape) == 1:
+            c = c.unsqueeze(-1).repeat((1, 2))
+        self.c = c.float().to(self.poses.device)
+        self._cam_cache = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _scene(self, fp32_maps: bool):
+        """pnr_scene view of the encoded state (+ the tensors that must stay alive during the call)."""
+        n_views = self.poses.shape[0]
+        NS = self.num_views_per_obj
+        SB = n_views // NS
+        dev = self.poses.device
+        if self._cam_cache is None:
+            def per_view(t):     # (1|SB, 2) -> (SB*NS, 2): repeat_interleave over views (models.py:225-230)
+                t = t.to(dev).float()
+                if t.shape[0] == 1:
+                    return t.expand(n_views, 2).contiguous()
+                if t.shape[0] == SB:
+                    return t.unsqueeze(1).expand(SB, NS, 2).reshape(n_views, 2).contiguous()
+                if t.shape[0] == n_views:
+                    return t.contiguous()
+                raise AssertionError(f"focal/c has {t.shape[0]} rows for {SB} objects x {NS} views")
+            self._cam_cache = (self.poses.contiguous(), per_view(self.focal), per_view(self.c),
+                               float(self.image_shape[0]), float(self.image_shape[1]),
+                               float(self.encoder.latent_scaling[0]), float(self.encoder.latent_scaling[1]))
+        poses, focal, center, iw, ih, lsx, lsy = self._cam_cache
+        feat = self.encoder.packed_latent(fp32=fp32_maps)
+        assert feat.shape[0] == n_views, "encoder.latent and poses disagree on the number of views"
+        sc = _lib.Scene()
+        sc.feat, sc.poses, sc.focal, sc.center = feat.data_ptr(), poses.data_ptr(), focal.data_ptr(), center.data_ptr()
+        sc.SB, sc.NS, sc.C, sc.Hl, sc.Wl = SB, NS, feat.shape[3], feat.shape[1], feat.shape[2]
+        sc.feat_fp32 = int(fp32_maps)
+        sc.image_w, sc.image_h, sc.lat_scale_x, sc.lat_scale_y = iw, ih, lsx, lsy
+        return sc, (feat, poses, focal, center)
+
+    def _mlp(self, coarse):
+        return self.mlp_coarse if (coarse or self.mlp_fine is None) else self.mlp_fine
+
+    def _run_field(self, pts: "_lib.Points", SB: int, P: int, coarse: bool, keep) -> torch.Tensor:
+        dev = self.poses.device
+        _lib.require_device(dev)
+        lib = _lib.load()
+        mlp = self._mlp(coarse)
+        out = torch.empty(SB, P, 4, device=dev, dtype=torch.float32)
+        if P == 0:
+            return out
+        launches = 0
+        with torch.cuda.device(dev):
+            if self.precision == "bf16":
+                sc, keep2 = self._scene(fp32_maps=False)
+                rc = lib.pnr_field_forward(sc, pts, mlp.c_params(), mlp.packed().data_ptr(), out.data_ptr(), None, 0,
+                                           _lib.PREC_BF16, self.code.num_freqs, self.code.freq_factor,
+                                           _lib.stream_ptr(dev))
+                _lib.check(rc, "pnr_field_forward(bf16)")
+                launches = lib.pnr_last_launch_count()
+            elif self.precision == "fp32":
+                sc, keep2 = self._scene(fp32_maps=True)
+                cp = mlp.c_params()
+                ws_bytes = lib.pnr_field_workspace_bytes(sc, pts, _lib.PREC_FP32)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                rc = lib.pnr_field_forward(sc, pts, cp, None, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                           _lib.PREC_FP32, self.code.num_freqs, self.code.freq_factor,
+                                           _lib.stream_ptr(dev))
+                _lib.check(rc, "pnr_field_forward(fp32)")
+                launches = lib.pnr_last_launch_count()
+            else:
+                raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+        self.last_launches = launches
+        return out
+
+    def forward(self, xyz, coarse=True, viewdirs=None, far=False):
+        """(r, g, b, sigma) at world points xyz (SB, B, 3) given view directions (SB, B, 3) -> (SB, B, 4)."""
+        SB, B, _ = xyz.shape
+        assert viewdirs is not None
+        _lib.require_cuda(xyz, "xyz")
+        if torch.is_grad_enabled() and (xyz.requires_grad or any(p.requires_grad for p in self._mlp(coarse).parameters())):
+            if self.training:
+                raise NotImplementedError("PixelNeRFNet (B200 path): backward is not built yet; wrap inference in "
+                                          "torch.no_grad() (the training step is SURVEY.md section 7 step 7)")
+        xyz = xyz.detach().contiguous().float()
+        viewdirs = viewdirs.detach().reshape(SB, B, 3).contiguous().float()
+        assert SB * self.num_views_per_obj == self.poses.shape[0], "call encode() first"
+        outs = []
+        step = B if self.precision == "bf16" else max(1, self.fp32_chunk_points // max(SB * self.num_views_per_obj, 1))
+        for b0 in range(0, max(B, 1), max(step, 1)):
+            xs, ds = xyz[:, b0:b0 + step].contiguous(), viewdirs[:, b0:b0 + step].contiguous()
+            pts = _lib.Points()
+            pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = xs.data_ptr(), ds.data_ptr(), 0, xs.shape[1], 0
+            outs.append(self._run_field(pts, SB, xs.shape[1], coarse, (xs, ds)))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+    def field_from_rays(self, rays, z, coarse=True, sb=1):
+        """Renderer fast path: evaluate the field at o + z*d for rays (SB*B, 8), z (SB*B, K) without ever
+        materialising the points (nerf.py:191-222 folded into the kernel's point fetch).  -> (SB*B, K, 4)."""
+        Bt, K = z.shape
+        assert Bt % sb == 0
+        Bp = Bt // sb
+        rays = rays.contiguous().float()
+        z = z.contiguous().float()
+        if self.precision == "bf16":
+            pts = _lib.Points()
+            pts.rays, pts.z, pts.mode, pts.P, pts.K = rays.data_ptr(), z.data_ptr(), 1, Bp * K, K
+            return self._run_field(pts, sb, Bp * K, coarse, (rays, z)).reshape(Bt, K, 4)
+        # fp32 check path: bound the workspace by chunking rays (results do not depend on the chunking)
+        step = max(1, self.fp32_chunk_points // max(K * self.num_views_per_obj * sb, 1))
+        outs = []
+        r3, z3 = rays.reshape(sb, Bp, 8), z.reshape(sb, Bp, K)
+        for b0 in range(0, Bp, step):
+            rc, zc = r3[:, b0:b0 + step].contiguous(), z3[:, b0:b0 + step].contiguous()
+            n = rc.shape[1]
+            pts = _lib.Points()
+            pts.rays, pts.z, pts.mode, pts.P, pts.K = rc.data_ptr(), zc.data_ptr(), 1, n * K, K
+            outs.append(self._run_field(pts, sb, n * K, coarse, (rc, zc)).reshape(sb, n, K, 4))
+        return torch.cat(outs, dim=1).reshape(Bt, K, 4)
+
+    # ------------------------------------------------------------------------------------------------
+    def load_weights(self, args, opt_init=False, strict=True, device=None):
+        """checkpoints/<name>/pixel_nerf_{init,latest} (models.py:320-349)."""
+        if opt_init and not args.resume:
+            return
+        ckpt_name = "pixel_nerf_init" if opt_init or not args.resume else "pixel_nerf_latest"
+        model_path = "%s/%s/%s" % (args.checkpoints_path, args.name, ckpt_name)
+        if device is None:
+            device = self.poses.device
+        if os.path.exists(model_path):
+            print("Load", model_path)
+            self.load_state_dict(torch.load(model_path, map_location=device), strict=strict)
+        elif not opt_init:
+            warnings.warn(("WARNING: {} does not exist, not loaded!! Model will be re-initialized.\n"
+                           "If you are trying to load a pretrained model, STOP since it's not in the right place. "
+                           "If training, unless you are startin a new experiment, please remember to pass --resume."
+                           ).format(model_path))
+        return self
+
+    def save_weights(self, args, opt_init=False, epochNum=""):
+        """models.py:351-370."""
+        from shutil import copyfile
+        ckpt_name = "pixel_nerf_init" if opt_init else "pixel_nerf_latest"
+        backup_name = "pixel_nerf_init_backup" if opt_init else "pixel_nerf_backup" + epochNum
+        ckpt_path = osp.join(args.checkpoints_path, args.name, ckpt_name)
+        ckpt_backup_path = osp.join(args.checkpoints_path, args.name, backup_name)
+        if osp.exists(ckpt_path):
+            copyfile(ckpt_path, ckpt_backup_path)
+        if epochNum == "":
+            torch.save(self.state_dict(), ckpt_path)
+        return self

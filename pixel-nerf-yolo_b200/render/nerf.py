@@ -1,0 +1,197 @@
+"""NeRFRenderer: drop-in for ``src/render/nerf.py`` on the sm_100a ray-tile kernels.
+
+One ``forward`` = sample_coarse -> field (coarse MLP) -> composite -> sample_fine + sample_fine_depth +
+sort -> field (fine MLP) -> composite, i.e. nerf.py:257-309, with every stage a CUDA kernel of the C-ABI
+library and the sample positions never materialised (the field kernel computes o + z*d itself).
+Random numbers are drawn with the same four torch calls, in the same order, as the reference
+(nerf.py:117,141,147,164), so a run seeded like the reference consumes the generator identically;
+``noise_override`` lets tests feed identical noise to the CPU oracle.
+"""
+import torch
+
+from .. import _lib
+from ..conf import DotMap
+
+
+class _RenderWrapper(torch.nn.Module):
+    """nerf.py:21-48: binds a network to a renderer; call signature ``(rays, want_weights=False)``."""
+
+    def __init__(self, net, renderer, simple_output):
+        super().__init__()
+        self.net = net
+        self.renderer = renderer
+        self.simple_output = simple_output
+
+    def forward(self, rays, want_weights=False):
+        if rays.shape[0] == 0:
+            return (torch.zeros(0, 3, device=rays.device), torch.zeros(0, device=rays.device))
+        outputs = self.renderer(self.net, rays, want_weights=want_weights and not self.simple_output)
+        if self.simple_output:
+            lvl = outputs.fine if self.renderer.using_fine else outputs.coarse
+            return lvl.rgb, lvl.depth
+        return outputs.toDict()
+
+
+class NeRFRenderer(torch.nn.Module):
+    def __init__(self, n_coarse=128, n_fine=0, n_fine_depth=0, noise_std=0.0, depth_std=0.01,
+                 eval_batch_size=100000, white_bkgd=False, lindisp=False, sched=None):
+        super().__init__()
+        self.n_coarse = n_coarse
+        self.n_fine = n_fine
+        self.n_fine_depth = n_fine_depth
+        self.noise_std = noise_std
+        self.depth_std = depth_std
+        self.eval_batch_size = eval_batch_size     # kept for API compatibility; the fused path never chunks
+        self.white_bkgd = white_bkgd
+        self.lindisp = lindisp
+        if lindisp:
+            print("Using linear displacement rays")
+        self.using_fine = n_fine > 0
+        self.sched = sched
+        if sched is not None and len(sched) == 0:
+            self.sched = None
+        self.register_buffer("iter_idx", torch.tensor(0, dtype=torch.long), persistent=True)
+        self.register_buffer("last_sched", torch.tensor(0, dtype=torch.long), persistent=True)
+        self.noise_override = None      # optional dict(coarse, fine_u, fine_jitter, depth) of device tensors
+        self.last_launches = 0          # kernels launched by the last forward (bench.py's gpu_launches)
+
+    # ---- stage wrappers (public so the parity tests can drive each reference method) -------------------
+    def _steps(self, device):
+        step = 1.0 / self.n_coarse
+        return torch.linspace(0, 1 - step, self.n_coarse).to(device)       # CPU linspace: same bits as the oracle
+
+    def sample_coarse(self, rays, noise=None):
+        """nerf.py:104-124.  rays (B, 8) -> z (B, Kc)."""
+        lib = _lib.load()
+        B = rays.shape[0]
+        dev = rays.device
+        if noise is None:
+            noise = torch.rand(B, self.n_coarse, device=dev, dtype=torch.float32)
+        z = torch.empty(B, self.n_coarse, device=dev, dtype=torch.float32)
+        steps = self._steps(dev)
+        with torch.cuda.device(dev):
+            rc = lib.pnr_sample_coarse(rays.data_ptr(), steps.data_ptr(), noise.contiguous().data_ptr(), z.data_ptr(),
+                                       B, self.n_coarse, int(self.lindisp), _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_sample_coarse")
+        self.last_launches += lib.pnr_last_launch_count()
+        return z
+
+    def composite_values(self, out, z, rays, want_weights=True):
+        """nerf.py:184-188,229-255 given the field values ``out`` (B, K, 4)."""
+        lib = _lib.load()
+        B, K = z.shape
+        dev = z.device
+        w = torch.empty(B, K, device=dev, dtype=torch.float32) if want_weights else None
+        rgb = torch.empty(B, 3, device=dev, dtype=torch.float32)
+        depth = torch.empty(B, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            rc = lib.pnr_composite(out.contiguous().data_ptr(), z.data_ptr(), rays.data_ptr(), _lib.ptr(w), rgb.data_ptr(),
+                                   depth.data_ptr(), B, K, int(bool(self.white_bkgd)), _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_composite")
+        self.last_launches += lib.pnr_last_launch_count()
+        return w, rgb, depth
+
+    def resample(self, rays, z_coarse, weights, depth, u=None, jitter=None, gauss=None, debug=False):
+        """sample_fine + sample_fine_depth + cat + sort (nerf.py:126-167, 290-301) -> z (B, Kc + n_fine)."""
+        lib = _lib.load()
+        B = rays.shape[0]
+        dev = rays.device
+        kf, kfd = self.n_fine - self.n_fine_depth, self.n_fine_depth
+        if kf > 0:
+            if u is None:
+                u = torch.rand(B, kf, dtype=torch.float32, device=dev)
+            if jitter is None:
+                jitter = torch.rand_like(u)
+        if kfd > 0 and gauss is None:
+            gauss = torch.randn(B, kfd, dtype=torch.float32, device=dev)
+        z_out = torch.empty(B, self.n_coarse + kf + kfd, device=dev, dtype=torch.float32)
+        dbg = None
+        if debug:
+            dbg = (torch.empty(B, kf, device=dev, dtype=torch.int32), torch.empty(B, kf, device=dev),
+                   torch.empty(B, kfd, device=dev))
+        c = lambda t: None if t is None else t.contiguous().data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.pnr_sample_fine(c(weights), c(depth), rays.data_ptr(), z_coarse.data_ptr(), c(u), c(jitter), c(gauss),
+                                     z_out.data_ptr(), c(dbg[0]) if dbg else None, c(dbg[1]) if dbg else None,
+                                     c(dbg[2]) if dbg else None, B, self.n_coarse, kf, kfd, float(self.depth_std),
+                                     int(self.lindisp), _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_sample_fine")
+        self.last_launches += lib.pnr_last_launch_count()
+        return (z_out, dbg) if debug else z_out
+
+    def _field(self, model, rays, z, coarse, sb):
+        if not hasattr(model, "field_from_rays"):
+            raise TypeError("NeRFRenderer (B200 path) renders pixel_nerf_yolo_b200.model.PixelNeRFNet instances "
+                            "only: the per-point model call of the reference is fused into one kernel and there "
+                            "is no generic-callable fallback")
+        out = model.field_from_rays(rays, z, coarse=coarse, sb=sb)
+        self.last_launches += getattr(model, "last_launches", 0)
+        return out
+
+    # ---- nerf.py:257-309 -----------------------------------------------------------------------------
+    def forward(self, model, rays, want_weights=False):
+        if self.sched is not None and self.last_sched.item() > 0:
+            self.n_coarse = self.sched[1][self.last_sched.item() - 1]
+            self.n_fine = self.sched[2][self.last_sched.item() - 1]
+        assert len(rays.shape) == 3
+        _lib.require_cuda(rays, "rays")
+        _lib.require_device(rays.device)
+        if self.training and self.noise_std > 0.0:
+            raise NotImplementedError("NeRFRenderer (B200 path): noise_std > 0 is not built (no shipped conf uses it)")
+        self.last_launches = 0
+        sb = rays.shape[0]
+        rays = rays.reshape(-1, 8).contiguous().float()
+        nz = self.noise_override or {}
+        with torch.no_grad():
+            z_coarse = self.sample_coarse(rays, nz.get("coarse"))
+            out_c = self._field(model, rays, z_coarse, True, sb)
+            need_w = want_weights or (self.using_fine and self.n_fine - self.n_fine_depth > 0)
+            coarse = self.composite_values(out_c, z_coarse, rays, want_weights=need_w)
+            outputs = DotMap(coarse=self._format_outputs(coarse, sb, want_weights))
+            if self.using_fine:
+                z_all = self.resample(rays, z_coarse, coarse[0], coarse[2], nz.get("fine_u"), nz.get("fine_jitter"),
+                                      nz.get("depth"))
+                out_f = self._field(model, rays, z_all, False, sb)
+                fine = self.composite_values(out_f, z_all, rays, want_weights=want_weights)
+                outputs.fine = self._format_outputs(fine, sb, want_weights)
+        return outputs
+
+    def _format_outputs(self, rendered, sb, want_weights=False):
+        weights, rgb, depth = rendered
+        if sb > 0:
+            rgb = rgb.reshape(sb, -1, 3)
+            depth = depth.reshape(sb, -1)
+            if weights is not None:
+                weights = weights.reshape(sb, -1, weights.shape[-1])
+        ret = DotMap(rgb=rgb, depth=depth)
+        if want_weights:
+            ret.weights = weights
+        return ret
+
+    def sched_step(self, steps=1):
+        """nerf.py:324-344."""
+        if self.sched is None:
+            return
+        self.iter_idx += steps
+        while self.last_sched.item() < len(self.sched[0]) and self.iter_idx.item() >= self.sched[0][self.last_sched.item()]:
+            self.n_coarse = self.sched[1][self.last_sched.item()]
+            self.n_fine = self.sched[2][self.last_sched.item()]
+            print("INFO: NeRF sampling resolution changed on schedule ==> c", self.n_coarse, "f", self.n_fine)
+            self.last_sched += 1
+
+    @classmethod
+    def from_conf(cls, conf, white_bkgd=False, lindisp=False, eval_batch_size=100000):
+        return cls(conf.get_int("n_coarse", 128), conf.get_int("n_fine", 0), n_fine_depth=conf.get_int("n_fine_depth", 0),
+                   noise_std=conf.get_float("noise_std", 0.0), depth_std=conf.get_float("depth_std", 0.01),
+                   white_bkgd=conf.get_float("white_bkgd", white_bkgd), lindisp=lindisp,
+                   eval_batch_size=conf.get_int("eval_batch_size", eval_batch_size), sched=conf.get_list("sched", None))
+
+    def bind_parallel(self, net, gpus=None, simple_output=False):
+        """nerf.py:360-377.  With several GPUs the rays are sharded across devices with the weights and the
+        encoded scene replicated once (not per call, as DataParallel does); see ``dist.ShardedRenderer``."""
+        wrapped = _RenderWrapper(net, self, simple_output=simple_output)
+        if gpus is not None and len(gpus) > 1:
+            from ..dist import MultiDeviceRenderer
+            print("Using multi-GPU", gpus)
+            wrapped = MultiDeviceRenderer(wrapped, gpus)
+        return wrapped

@@ -1,0 +1,132 @@
+"""CPU-side tests: config parsing, C-ABI surface, sharding host logic (gloo, world_size 2), API shape."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_hocon_subset_parser(tmp_path):
+    from pixel_nerf_yolo_b200 import conf
+    (tmp_path / "base.conf").write_text(
+        "# comment\nmodel {\n  use_xyz = True  # trailing\n  code { num_freqs = 6\n freq_factor = 1.5 }\n"
+        "  mlp_coarse { type = resnet\n n_blocks = 3 }\n}\nrenderer { sched = []\n white_bkgd = True }\n")
+    (tmp_path / "exp").mkdir()
+    (tmp_path / "exp" / "child.conf").write_text(
+        'include required("../base.conf")\nmodel {\n mlp_coarse{\n n_blocks = 5\n combine_layer = 3 }\n}\n'
+        "yolo { anchors = [\n [[0.02, 0.03], [0.04, 0.07]],\n [[0.07, 0.15], [0.15, 0.11]]\n ]\n scale = [0.5, 0.47407] }\n")
+    c = conf.parse_file(str(tmp_path / "exp" / "child.conf"))
+    assert c["model.mlp_coarse.n_blocks"] == 5 and c["model"]["mlp_coarse"].get_string("type") == "resnet"
+    assert c.get_int("model.mlp_coarse.combine_layer") == 3 and c["model"].get_bool("use_xyz") is True
+    assert c["model.code"].get_float("freq_factor") == 1.5 and c.get_list("renderer.sched") == []
+    assert c["yolo.anchors"][1][0] == [0.07, 0.15] and c["yolo"].get_list("scale") == [0.5, 0.47407]
+    assert "model.mlp_fine" not in c and c.get_int("model.missing", 7) == 7
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/conf"), reason="reference confs only exist in the build container")
+def test_parses_every_reference_conf():
+    from pixel_nerf_yolo_b200 import conf
+    for name in ("default.conf", "default_mv.conf", "exp/dtu.conf", "exp/multi_obj.conf", "exp/sn64.conf",
+                 "exp/sn64_unseen.conf", "exp/srn.conf", "exp/yolo.conf"):
+        c = conf.parse_file(os.path.join("/root/reference/conf", name))
+        assert c.get_string("model.mlp_coarse.type") == "resnet", name
+        assert c.get_int("renderer.n_coarse") in (64, 128), name
+    c = conf.parse_file("/root/reference/conf/exp/yolo.conf")
+    assert c["yolo.anchors"][2][2] == [0.9, 0.78] and c.get_bool("model.mlp_coarse.yolo") is True
+    assert c.get_int("model.mlp_coarse.n_blocks") == 5 and c.get_string("model.encoder.backbone") == "custom"
+
+
+def test_dotmap_contract():
+    from pixel_nerf_yolo_b200.conf import DotMap
+    d = DotMap(coarse=DotMap(rgb=1))
+    assert len(d.fine) == 0 and d.coarse.rgb == 1 and d.toDict() == {"coarse": {"rgb": 1}, "fine": {}}
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads (no GPU needed) and exports exactly what include/pixelnerf_b200.h declares."""
+    from pixel_nerf_yolo_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "pixelnerf_b200.h")).read()
+    declared = set(re.findall(r"\b(pnr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pnr_version() == 1
+    # struct layouts agree with the header (sizes computed by the C compiler)
+    src = '#include "pixelnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu",sizeof(pnr_scene),sizeof(pnr_points),sizeof(pnr_mlp_params));}'
+    exe = os.path.join(ROOT, "pixel-nerf-yolo_b200", "csrc", "build", "sizes")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
+    sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_lib.Scene), ctypes.sizeof(_lib.Points), ctypes.sizeof(_lib.MlpParams)]
+
+
+def test_no_silent_cpu_fallback():
+    """Without a GPU the product path must raise, not compute on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU box")
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    from pixel_nerf_yolo_b200.model.code import PositionalEncoding
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        NeRFRenderer(64, 32, 16)(object(), torch.zeros(1, 4, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PositionalEncoding(6, 3, 1.5)(torch.zeros(3, 3))
+
+
+def test_unsupported_options_raise():
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.model.resnetfc import ResnetFC
+    from pixel_nerf_yolo_b200.model.encoder import SpatialEncoder
+    from pixel_nerf_yolo_b200.render.render_util import make_renderer
+    with pytest.raises(NotImplementedError):
+        ResnetFC(42, 4, d_latent=512, d_hidden=512, combine_type="max")
+    with pytest.raises(NotImplementedError):
+        ResnetFC(42, 4, d_latent=512, d_hidden=512, beta=100.0)
+    with pytest.raises(NotImplementedError):
+        SpatialEncoder("resnet34", pretrained=False, index_padding="border")
+    with pytest.raises(NotImplementedError):
+        make_renderer(ConfigTree.from_dict({"renderer": {"type": "yolo"}}))
+
+
+def test_model_api_and_state_dict_names():
+    from helpers import MODEL_CONF
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.model import make_model
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    import pixel_nerf_yolo_b200.synth as synth
+    net = make_model(ConfigTree.from_dict(MODEL_CONF))
+    sd = net.state_dict()
+    assert (net.d_in, net.d_latent, net.d_out) == (42, 512, 4)
+    for mlp in ("mlp_coarse", "mlp_fine"):
+        for k, v in synth.mlp_state(0).items():
+            assert tuple(sd[f"{mlp}.{k}"].shape) == tuple(v.shape)
+    assert "code._freqs" in sd and "code._phases" in sd and "poses" not in sd and "encoder.latent" not in sd
+    assert sum(p.numel() for p in net.parameters()) == 28161864
+    r = NeRFRenderer.from_conf(ConfigTree.from_dict({"n_coarse": 64, "n_fine": 32, "n_fine_depth": 16, "sched": []}))
+    assert set(r.state_dict()) == {"iter_idx", "last_sched"} and r.using_fine and r.sched is None
+
+
+def test_shard_bounds_cover_and_align():
+    from pixel_nerf_yolo_b200.dist import shard_bounds
+    for n in (0, 1, 31, 32, 33, 2048, 16384, 16385, 409600):
+        for world in (1, 2, 3, 4, 8):
+            b = shard_bounds(n, world)
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert all(s % 32 == 0 for s, _ in b if s < n)
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) < 2 * 32 or n < 32 * world   # last slice is clipped to n
+
+
+def test_sharded_render_two_ranks_gloo_matches_single():
+    """world_size-2 gloo run of ShardedRenderer: gathered output == the unsharded render, bit for bit."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", script],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_SHARD_OK" in r.stdout
