@@ -112,7 +112,7 @@ __global__ void positional_encoding_kernel(const float* __restrict__ x, float* _
     int r = q - k * 2 * d;
     float f = freq_factor * (float)(1 << k);
     float ph = r >= d ? 1.57079637050628662109375f : 0.0f;
-    v = sinf(__fadd_rn(ph, __fmul_rn(x[row * d + (r % d)], f)));
+    v = sinf(fmaf(x[row * d + (r % d)], f, ph));   // addcmul is a fused multiply-add in ATen
   }
   out[i] = v;
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ float zfeat_value(const Projection& p, int j, int num
     float x = d == 0 ? p.xr : (d == 1 ? p.yr : p.zr);
     float f = freq_factor * (float)(1 << k);
     float ph = r >= 3 ? 1.57079637050628662109375f : 0.0f;   // float32(pi/2), code.py:26-27
-    return sinf(__fadd_rn(ph, __fmul_rn(x, f)));              // sin(addcmul(phase, x, freq))
+    return sinf(fmaf(x, f, ph));                             // sin(addcmul(phase, x, freq)): ATen fuses the multiply-add
   }
   int d = j - n_pe;
   return d == 0 ? p.dx : (d == 1 ? p.dy : p.dz);
