@@ -154,6 +154,20 @@ int pnr_last_launch_count(void);
  * output; workspace: K/64 * 16 KiB, 1024-byte aligned.  N in {16,32,48,64}, K multiple of 64 <= 512. */
 int pnr_umma_selftest(const float* a, const float* b, float* d, void* workspace, int N, int K, void* stream);
 
+/* Design-aid micro-benchmark: per-SM cp.async.bulk ingest (16 KiB stages, `depth`-slot ring, `grid` CTAs streaming
+ * `n_stages` stages each from a buffer of `src_stages` stages).  out[grid] = elapsed SM cycles per CTA. */
+int pnr_ingest_bench(const void* src, int src_stages, int n_stages, int depth, int grid, long long* out,
+                     int n_prod, int n_cons, int stage_bytes, void* stream);
+
+/* Same through a 2-D tensor map (cp.async.bulk.tensor.2d), box = 64 x box_rows bf16, optional 128B swizzle. */
+int pnr_ingest_bench_tma(const void* src, int src_stages, int n_stages, int depth, int grid, long long* out,
+                         int box_rows, int swizzle, void* stream);
+
+/* Design-aid micro-benchmark: cycles for `iters` x 8 tcgen05.mma (kind::f16, bf16, K=16) of shape M x N issued
+ * back to back from shared-memory operands.  out[grid] = elapsed SM cycles per CTA. */
+int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid, long long* out, int commit_every,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ EXPORTS = [
     "pnr_sample_fine", "pnr_pack_features", "pnr_gather_encode", "pnr_mlp_pack_bytes", "pnr_mlp_pack",
     "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_umma_selftest",
     "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
+    "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench",
 ]
 
 
@@ -88,6 +89,9 @@ def load() -> C.CDLL:
     lib.pnr_resnetfc_forward.argtypes = [C.POINTER(MlpParams), vp, C.c_longlong, i32, i32, vp, vp, C.c_size_t, vp]
     lib.pnr_positional_encoding.argtypes = [vp, vp, C.c_longlong, i32, i32, f32, i32, vp]
     lib.pnr_index_features.argtypes = [C.POINTER(Scene), vp, i32, i32, vp, vp]
+    lib.pnr_ingest_bench.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
+    lib.pnr_ingest_bench_tma.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
+    lib.pnr_umma_bench.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)          # AttributeError here = header and library disagree
     if lib.pnr_version() != 1:
