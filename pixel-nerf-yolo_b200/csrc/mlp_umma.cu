@@ -668,14 +668,16 @@ static int make_sched(const pnr_mlp_params* p, Sched* s, const char* who) {
   return PNR_OK;
 }
 
-// Cluster size of the weight multicast: PNR_CLUSTER env (1, 2, 4 or 8) overrides the default.
+// Cluster size of the weight multicast: PNR_CLUSTER env (1, 2, 4 or 8) overrides the default of 1.  Measured on
+// B200: L2 is not the limiter of this kernel (the per-SM shared-memory fill + operand reads are), so multicast buys
+// nothing at the moment and clusters of 4/8 strand SMs (132/120 of 148 usable).
 static int cluster_size_setting() {
   static int cached = 0;
   if (cached == 0) {
-    int v = 4;
+    int v = 1;
     const char* e = getenv("PNR_CLUSTER");
     if (e) v = atoi(e);
-    if (v != 1 && v != 2 && v != 4 && v != 8) v = 4;
+    if (v != 1 && v != 2 && v != 4 && v != 8) v = 1;
     cached = v;
   }
   return cached;
