@@ -58,8 +58,22 @@ struct Sched {
   int KBz;        // d_latent / 64
 };
 enum { MAT_LIN_IN = 0, MAT_LINZ = 1, MAT_FC0 = 2, MAT_FC1 = 3, MAT_LIN_OUT = 4 };
+// lin_z consumes the latent operand in passes of <= 8 k-blocks (512 channels = the shared-memory latent tile):
+// one pass when d_latent <= 512 (the tile stays resident for lin_z[0..2]), several otherwise (re-gathered per pass).
+struct ZPos { int pass, mt, kbi, kp; };   // pass index, feature tile, k-block inside the pass, k-blocks in this pass
+__host__ __device__ inline int z_passes(const Sched& s);
+__host__ __device__ inline ZPos z_position(int KBz, int t) {
+  ZPos z;
+  z.pass = t / (kMTiles * 8);
+  const int tt = t - z.pass * kMTiles * 8;
+  z.kp = KBz - z.pass * 8 < 8 ? KBz - z.pass * 8 : 8;
+  z.mt = tt / z.kp;
+  z.kbi = tt - z.mt * z.kp;
+  return z;
+}
 struct StageSrc { int mat, blk, row0, k0; };
 
+__host__ __device__ inline int z_passes(const Sched& s) { return (s.KBz + 7) / 8; }
 __host__ __device__ inline int sched_total(const Sched& s) {
   return kMTiles + s.n_linz * kMTiles * s.KBz + s.n_blocks * 64 + kKBlocksH;
 }
@@ -94,7 +108,7 @@ __host__ __device__ inline StageSrc decode_stage(const Sched& sc, int s) {
   r.mat = g.kind; r.blk = g.blk;
   switch (g.kind) {
     case MAT_LIN_IN: r.row0 = g.t * 128; r.k0 = 0; break;
-    case MAT_LINZ: r.row0 = (g.t / sc.KBz) * 128; r.k0 = (g.t % sc.KBz) * 64; break;
+    case MAT_LINZ: { const ZPos z = z_position(sc.KBz, g.t); r.row0 = z.mt * 128; r.k0 = (z.pass * 8 + z.kbi) * 64; } break;
     case MAT_FC0:
     case MAT_FC1: r.row0 = ((g.t % 8) / 2) * 128; r.k0 = (g.t / 8) * 128 + (g.t % 2) * 64; break;   // chunk kc=t/8, tile (t%8)/2, half t%2
     default: r.row0 = 0; r.k0 = g.t * 64; break;
@@ -161,9 +175,9 @@ struct Smem {
   static constexpr uint32_t bars = zf + kOperandKB;
   static constexpr uint32_t prof = bars + 256;                            // 32 x 8 B debug counters
   static constexpr uint32_t prog = bars + 512;                            // per-stage MMA program, 8 B x kMaxStages
-  static constexpr uint32_t total = prog + 8 * 512;
+  static constexpr uint32_t total = prog + 8 * 1024;
 };
-constexpr int kMaxStages = 512;
+constexpr int kMaxStages = 1024;
 enum {
   B_W_FULL = 0, B_W_EMPTY = B_W_FULL + kStages, B_IN_READY = B_W_EMPTY + kStages, B_IN_FREE, B_X_FULL, B_H_FULL,
   B_AX_READY, B_AX_FREE = B_AX_READY + 2, B_AH_READY = B_AX_FREE + 2, B_AH_FREE = B_AH_READY + 2,
@@ -186,10 +200,17 @@ __device__ inline ProgEntry make_prog(const Sched& sc, int s, uint32_t sbase) {
       b_addr = sbase + Smem::zf; dcol = g.t * kNCol; acc = 0;
       if (g.t == 0) wait_id = B_IN_READY + 1;
       break;
-    case MAT_LINZ:
-      b_addr = sbase + Smem::lat + (g.t % sc.KBz) * kOperandKB; dcol = (g.t / sc.KBz) * kNCol;
-      if (last) { if (g.blk == sc.n_linz - 1) c1 = B_IN_FREE + 1; if (g.blk == 0) c2 = B_X_FULL + 1; }
-      break;
+    case MAT_LINZ: {
+      const ZPos z = z_position(sc.KBz, g.t);
+      const bool streaming = z_passes(sc) > 1;
+      const bool pass_first = z.mt == 0 && z.kbi == 0, pass_last = z.mt == kMTiles - 1 && z.kbi == z.kp - 1;
+      b_addr = sbase + Smem::lat + z.kbi * kOperandKB; dcol = z.mt * kNCol;
+      // resident latent tile: gathered once per tile (lin_in waits for it, the last lin_z frees it);
+      // streamed latent: every (lin_z, pass) waits for its own gather and frees the tile afterwards
+      if (streaming && pass_first && !(g.blk == 0 && z.pass == 0)) wait_id = B_IN_READY + 1;
+      if (pass_last && (streaming || g.blk == sc.n_linz - 1)) c1 = B_IN_FREE + 1;
+      if (last && g.blk == 0) c2 = B_X_FULL + 1;
+    } break;
     case MAT_FC0: {
       const int kc = g.t / 8, j = (g.t % 8) / 2, kk = g.t % 2;
       b_addr = sbase + Smem::ax + ((kc & 1) * 2 + kk) * kOperandKB; dcol = kHCol + j * kNCol; acc = (kc > 0 || kk > 0);
@@ -495,78 +516,85 @@ field_umma_kernel(const pnr_scene sc, const pnr_points q, const uint8_t* __restr
     const int gw = warp < 4 ? warp - 2 : warp - 6;   // 0..5
     uint32_t par_free = 1;                           // "empty"-type barrier: first wait passes
     const long long t_role0 = prof ? clock64() : 0;
+    const int n_pass = z_passes(sch);
+    const int fills = n_pass > 1 ? sch.n_linz * n_pass : 1;      // latent tile fills per tile (1 = resident)
     for (int grp = cluster_id; grp < n_groups; grp += n_clusters) {
       const int tile = grp * (int)CS + (int)crank;
       const int obj = tile / tiles_per_obj;
       const int p0 = (tile - obj * tiles_per_obj) * PP;
-      {
-        PROF_T0();
-        mbar_wait(bar(B_IN_FREE), par_free);
-        if (gw == 0) PROF_ADD(17);
-      }
-      par_free ^= 1;
-      for (int c = gw; c < kNCol; c += kGatherWarps) {
-        const int v = c / PP, p = c - v * PP;
-        const bool valid = (tile < n_tiles) && (v < NS) && (p0 + p < q.P);
-        Projection pr;
-        Taps tp;
-        const int view = obj * NS + (v < NS ? v : 0);
-        if (valid) {
-          float px, py, pz, vx, vy, vz;
-          fetch_point(q, (long long)obj * q.P + p0 + p, px, py, pz, vx, vy, vz);
-          pr = project_point(sc, view, px, py, pz, vx, vy, vz);
-          tp = make_taps(pr.ix, pr.iy, sc.Hl, sc.Wl, sc.C);
-        }
-        // z-feature row: 64 bf16 (d_in <= 64 used), two per lane
+      for (int fill = 0; fill < fills; ++fill) {
+        const int pass = fill % n_pass;
+        const int kp = sch.KBz - pass * 8 < 8 ? sch.KBz - pass * 8 : 8;     // k-blocks (64 channels each) in this pass
+        const int ch0 = pass * 512;
         {
-          const int j0 = lane * 2;
-          float a = 0.f, b = 0.f;
-          const int d_in = 6 * num_freqs + 6;
+          PROF_T0();
+          mbar_wait(bar(B_IN_FREE), par_free);
+          if (gw == 0) PROF_ADD(17);
+        }
+        par_free ^= 1;
+        for (int c = gw; c < kNCol; c += kGatherWarps) {
+          const int v = c / PP, p = c - v * PP;
+          const bool valid = (tile < n_tiles) && (v < NS) && (p0 + p < q.P);
+          Projection pr;
+          Taps tp;
+          const int view = obj * NS + (v < NS ? v : 0);
           if (valid) {
-            if (j0 < d_in) a = zfeat_value(pr, j0, num_freqs, freq_factor);
-            if (j0 + 1 < d_in) b = zfeat_value(pr, j0 + 1, num_freqs, freq_factor);
+            float px, py, pz, vx, vy, vz;
+            fetch_point(q, (long long)obj * q.P + p0 + p, px, py, pz, vx, vy, vz);
+            pr = project_point(sc, view, px, py, pz, vx, vy, vz);
+            tp = make_taps(pr.ix, pr.iy, sc.Hl, sc.Wl, sc.C);
           }
-          *reinterpret_cast<__nv_bfloat162*>(smem + Smem::zf + swz_offset(c, j0)) = __floats2bfloat162_rn(a, b);
-        }
-        // latent row: C = 512 channels, lane covers [16*lane, 16*lane+16) = two 16-byte chunks of k-block lane/4
-        {
-          float acc[16];
+          // z-feature row (first fill of the tile only): 64 bf16 (d_in <= 64 used), two per lane
+          if (fill == 0) {
+            const int j0 = lane * 2;
+            float a = 0.f, b = 0.f;
+            const int d_in = 6 * num_freqs + 6;
+            if (valid) {
+              if (j0 < d_in) a = zfeat_value(pr, j0, num_freqs, freq_factor);
+              if (j0 + 1 < d_in) b = zfeat_value(pr, j0 + 1, num_freqs, freq_factor);
+            }
+            *reinterpret_cast<__nv_bfloat162*>(smem + Smem::zf + swz_offset(c, j0)) = __floats2bfloat162_rn(a, b);
+          }
+          // latent row: channels [ch0, ch0 + 64*kp); lane covers 16 of them = two 16-byte chunks of k-block lane/4
+          if ((lane >> 2) < kp) {
+            float acc[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-          if (valid) {
-            const __nv_bfloat16* fmap = (const __nv_bfloat16*)sc.feat + (size_t)view * sc.Hl * sc.Wl * sc.C + lane * 16;
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            if (valid) {
+              const __nv_bfloat16* fmap = (const __nv_bfloat16*)sc.feat + (size_t)view * sc.Hl * sc.Wl * sc.C + ch0 + lane * 16;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (tp.off[k] < 0) continue;
-              const uint4* src = reinterpret_cast<const uint4*>(fmap + tp.off[k]);
-              const uint4 r0 = __ldg(src), r1 = __ldg(src + 1);
-              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+              for (int k = 0; k < 4; ++k) {
+                if (tp.off[k] < 0) continue;
+                const uint4* src = reinterpret_cast<const uint4*>(fmap + tp.off[k]);
+                const uint4 r0 = __ldg(src), r1 = __ldg(src + 1);
+                const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+                const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
-                acc[2 * i] += tp.w[k] * f0.x; acc[2 * i + 1] += tp.w[k] * f0.y;
-                acc[8 + 2 * i] += tp.w[k] * f1.x; acc[8 + 2 * i + 1] += tp.w[k] * f1.y;
+                for (int i = 0; i < 4; ++i) {
+                  float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
+                  acc[2 * i] += tp.w[k] * f0.x; acc[2 * i + 1] += tp.w[k] * f0.y;
+                  acc[8 + 2 * i] += tp.w[k] * f1.x; acc[8 + 2 * i + 1] += tp.w[k] * f1.y;
+                }
               }
             }
-          }
-          uint4 o0, o1;
-          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+            uint4 o0, o1;
+            __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+            __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            q0[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-            q1[i] = __floats2bfloat162_rn(acc[8 + 2 * i], acc[8 + 2 * i + 1]);
+            for (int i = 0; i < 4; ++i) {
+              q0[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+              q1[i] = __floats2bfloat162_rn(acc[8 + 2 * i], acc[8 + 2 * i + 1]);
+            }
+            uint8_t* kb_base = smem + Smem::lat + (lane >> 2) * kOperandKB;
+            const int k_in = (lane & 3) * 16;
+            *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in)) = o0;
+            *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in + 8)) = o1;
           }
-          uint8_t* kb_base = smem + Smem::lat + (lane >> 2) * kOperandKB;
-          const int k_in = (lane & 3) * 16;
-          *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in)) = o0;
-          *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in + 8)) = o1;
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_IN_READY));
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_IN_READY));
     }
     if (prof && gw == 0 && lane == 0) prof[16] += clock64() - t_role0;
   }
@@ -691,8 +719,7 @@ int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   PNR_REQUIRE(packed, PNR_ERR_ARG, "field_forward_umma: packed weights missing (call pnr_mlp_pack)");
   PNR_REQUIRE(((uintptr_t)packed & 1023) == 0, PNR_ERR_ARG, "field_forward_umma: packed blob must be 1024-byte aligned");
   PNR_REQUIRE(!sc->feat_fp32, PNR_ERR_ARG, "field_forward_umma: needs bf16 channels-last feature maps");
-  PNR_REQUIRE(sc->C == 512 && mp->d_latent == 512, PNR_ERR_UNSUPPORTED,
-              "field_forward_umma: latent size %d (this build keeps a 512-channel latent tile resident)", sc->C);
+  PNR_REQUIRE(sc->C == mp->d_latent, PNR_ERR_ARG, "field_forward_umma: feature maps have %d channels, the MLP expects %d", sc->C, mp->d_latent);
   PNR_REQUIRE(mp->d_in == 6 * num_freqs + 6, PNR_ERR_ARG, "field_forward_umma: d_in/num_freqs mismatch");
   PNR_REQUIRE(sc->NS >= 1 && sc->NS <= 8 && sc->NS != 7, PNR_ERR_UNSUPPORTED, "field_forward_umma: NS=%d source views", sc->NS);
   if ((long long)sc->SB * q->P == 0) return PNR_OK;

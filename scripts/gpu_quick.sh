@@ -2,7 +2,7 @@
 # quick correctness + speed check of the fused kernel
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests -m gpu -q --timeout 300 -k "umma or field or render or edge or full_image" > gpurun_out/test_quick.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 -k "umma or field or render or edge or full_image or latent_widths" > gpurun_out/test_quick.log 2>&1
 echo "tests exit $? $(tail -1 gpurun_out/test_quick.log)"
 for cs in ${SWEEP:-1 2}; do
   PNR_CLUSTER=$cs timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_q$cs.log 2>gpurun_out/bench_q$cs.err

@@ -224,6 +224,29 @@ def test_field_matches_oracle(lib, precision, tol, num_objs, num_views, P):
     assert ref[..., 3].max() > 0.5 and ref[..., :3].std() > 0.01          # the comparison is not vacuous
 
 
+@pytest.mark.parametrize("C,enc", [(1792, {"backbone": "custom", "pretrained": False, "index_padding": "zeros"}),
+                                   (256, {"backbone": "resnet34", "pretrained": False, "num_layers": 3, "index_padding": "zeros"}),
+                                   (1024, {"backbone": "resnet34", "pretrained": False, "num_layers": 5, "index_padding": "zeros"})])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_field_other_latent_widths(lib, precision, tol, C, enc):
+    """BASELINE config 4 shape: YOLO-sized 1792-channel maps (and 256 / 1024-channel resnet pyramids): lin_z is streamed
+    through the 512-channel latent tile in passes."""
+    conf = dict(H.MODEL_CONF)
+    conf["encoder"] = enc
+    scene = H.make_scene_dict(num_objs=1, num_views=3, feat=12, C=C)
+    net = H.build_net(scene, precision=precision, model_conf=conf)
+    g = torch.Generator().manual_seed(C)
+    P = 150
+    xyz = (torch.rand(1, P, 3, generator=g) - 0.5) * 0.9
+    dirs = torch.nn.functional.normalize(torch.randn(1, P, 3, generator=g), dim=-1)
+    with torch.no_grad():
+        out = net(xyz.cuda(), coarse=True, viewdirs=dirs.cuda()).cpu()
+    ref = O.field_forward(H.oracle_scene(scene), synth.mlp_state(1, d_latent=C), xyz, dirs)
+    err_rgb = (out[..., :3] - ref[..., :3]).abs().max().item()
+    err_sig = ((out[..., 3] - ref[..., 3]).abs() / (1 + ref[..., 3].abs())).max().item()
+    assert err_rgb < tol and err_sig < tol, (err_rgb, err_sig)
+
+
 # ------------------------------------------------------------------------------------------------ render
 def _render_cuda(net, rays, noise, **kw):
     r = _renderer(**kw)
