@@ -116,15 +116,29 @@ __host__ __device__ inline StageSrc decode_stage(const Sched& sc, int s) {
   return r;
 }
 
-struct PackOffsets { size_t stages, bias_x, bias_h, bias_out, total; };
-static PackOffsets pack_offsets(const Sched& s) {
+// CTA-pair kernel (mlp_umma_pair.cu)
+size_t pair_stream_bytes(const pnr_mlp_params* p);
+int pair_pack(const pnr_mlp_params* p, uint8_t* stream, cudaStream_t st);
+int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const uint8_t* stream,
+                       const float* bx, const float* bh, const float* bo, float* out, int num_freqs, float freq_factor,
+                       int raw, cudaStream_t st);
+
+struct PackOffsets { size_t stages, bias_x, bias_h, bias_out, pair_stream, total; };
+static PackOffsets pack_offsets(const Sched& s, const pnr_mlp_params* p) {
   PackOffsets o;
   o.stages = kPackHeader;
   o.bias_x = o.stages + (size_t)sched_total(s) * kStageBytes;
   o.bias_h = o.bias_x + (size_t)(s.n_blocks + 1) * kHidden * sizeof(float);
   o.bias_out = o.bias_h + (size_t)s.n_blocks * kHidden * sizeof(float);
-  o.total = o.bias_out + 128 * sizeof(float);
+  o.pair_stream = (o.bias_out + 128 * sizeof(float) + 1023) & ~(size_t)1023;     // second copy of the weights, CTA-pair order
+  o.total = o.pair_stream + pair_stream_bytes(p);
   return o;
+}
+// PNR_PAIR=0 selects the single-CTA kernel, anything else (default) the CTA-pair kernel.
+static bool use_pair_kernel() {
+  static int cached = -1;
+  if (cached < 0) { const char* e = getenv("PNR_PAIR"); cached = (e && atoi(e) == 0) ? 0 : 1; }
+  return cached == 1;
 }
 
 __global__ void pack_stages_kernel(pnr_mlp_params mp, Sched sc, uint8_t* __restrict__ stages) {
@@ -734,17 +748,19 @@ int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   int cs = cluster_size_setting();
   while (cs > 1 && n_tiles < cs * 2) cs >>= 1;          // tiny problems: do not pad most of a cluster with dummy tiles
   long long* prof_dev = nullptr;
-  if (getenv("PNR_PROF")) {
+  if (getenv("PNR_PROF") && !use_pair_kernel()) {
     cudaMalloc(&prof_dev, (size_t)4096 * 32 * sizeof(long long));
     cudaMemset(prof_dev, 0, (size_t)4096 * 32 * sizeof(long long));
     cudaMemcpyToSymbol(g_prof, &prof_dev, sizeof(prof_dev));
   }
-  const PackOffsets po = pack_offsets(sch);
+  const PackOffsets po = pack_offsets(sch, mp);
   const uint8_t* blob = (const uint8_t*)packed;
   const uint8_t* stages = blob + po.stages;
   const float* bx = (const float*)(blob + po.bias_x);
   const float* bh = (const float*)(blob + po.bias_h);
   const float* bo = (const float*)(blob + po.bias_out);
+  if (use_pair_kernel())
+    return field_forward_pair(sc, q, mp, blob + po.pair_stream, bx, bh, bo, out, num_freqs, freq_factor, raw, st);
 #define PNR_LAUNCH_NS(NSV)                                                                                   \
   case NSV: {                                                                                                \
     auto kern = field_umma_kernel<NSV>;                                                                      \
@@ -801,7 +817,7 @@ using namespace pnr;
 extern "C" size_t pnr_mlp_pack_bytes(const pnr_mlp_params* p) {
   Sched s;
   if (make_sched(p, &s, "pnr_mlp_pack_bytes")) return 0;
-  return pack_offsets(s).total;
+  return pack_offsets(s, p).total;
 }
 
 extern "C" int pnr_mlp_pack(const pnr_mlp_params* p, void* packed, void* stream) {
@@ -814,9 +830,11 @@ extern "C" int pnr_mlp_pack(const pnr_mlp_params* p, void* packed, void* stream)
   for (int b = 0; b < p->n_blocks; ++b)
     PNR_REQUIRE(p->fc0_w[b] && p->fc0_b[b] && p->fc1_w[b] && p->fc1_b[b], PNR_ERR_ARG, "pnr_mlp_pack: null block %d", b);
   for (int b = 0; b < s.n_linz; ++b) PNR_REQUIRE(p->linz_w[b] && p->linz_b[b], PNR_ERR_ARG, "pnr_mlp_pack: null lin_z %d", b);
-  const PackOffsets po = pack_offsets(s);
+  const PackOffsets po = pack_offsets(s, p);
   uint8_t* blob = (uint8_t*)packed;
   cudaStream_t st = (cudaStream_t)stream;
+  rc = pair_pack(p, blob + po.pair_stream, st);
+  if (rc) return rc;
   pack_stages_kernel<<<sched_total(s), 256, 0, st>>>(*p, s, blob + po.stages);
   PNR_CHECK_LAUNCH("pack_stages_kernel");
   pack_bias_kernel<<<1, kHidden, 0, st>>>(*p, s, (float*)(blob + po.bias_x), (float*)(blob + po.bias_h),

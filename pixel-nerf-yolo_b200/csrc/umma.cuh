@@ -78,7 +78,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  The spin lives out of line so
 // that the (latency-critical, single-thread) MMA issue loop stays small.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -222,6 +222,125 @@ __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r) {
 #pragma unroll
   for (int c = 0; c < NCOLS; c += 16) tmem_st16(taddr + c, r + c);
   tmem_st_wait();
+}
+
+}  // namespace umma
+}  // namespace pnr
+
+// =====================================================================================================
+// CTA-pair (cta_group::2) building blocks: one tcgen05.mma spans the two SMs of a cluster of 2.  A (M=256) is split
+// by rows and B (N) by rows between the two CTAs, each reading its half from ITS OWN shared memory at the same
+// offset; each CTA's TMEM receives its 128 rows x N columns of D.  Issued by one thread of the leader CTA (rank 0).
+// =====================================================================================================
+namespace pnr {
+namespace umma {
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {   // address of the same offset in a peer CTA
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+// arrive (count 1) on an mbarrier anywhere in the cluster; release at cluster scope publishes this thread's prior writes
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// same without the (costly, ~1k cycles) cluster-scope release: only valid after an explicit fence that already made
+// the data visible where it will be consumed (fence.proxy.async on the writer side)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {       // acquire at cluster scope
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("pnr: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait_cluster(bar, parity)) mbar_wait_cluster_slow(bar, parity);
+}
+__device__ __forceinline__ void fence_proxy_async_all() {   // generic-proxy writes (any space) -> async proxy; expensive (~2k cycles)
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_cluster() {   // generic-proxy writes to shared memory of any CTA of the cluster
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {   // one full warp in EACH CTA, same dst offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// kind::f16, A=B=bf16, D=f32, both K-major, M=256 (pair), N=n
+__host__ __device__ __forceinline__ uint32_t instr_desc_bf16_2sm(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_kblock_desc_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                    bool accumulate_first) {
+#pragma unroll
+  for (int ks = 0; ks < kBlockK / kUmmaK; ++ks)
+    mma_bf16_2sm(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (accumulate_first || ks > 0) ? 1u : 0u);
+}
+// completion of all prior tcgen05 ops of this thread -> arrive on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+// 2-D tensor-map TMA load into THIS CTA's shared memory whose completion is signalled on the LEADER CTA's mbarrier
+// (same offset; bit 24 of a shared::cluster address selects the CTA of the pair)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// 8x8 transpose across the 8 lanes of a lane group (lanes 8g..8g+7): in: a[k] = value of THIS lane for item k;
+// out: a[k] = value of lane (8g + k) for item (lane % 8).  Three butterfly rounds of 4 shuffles, static register indices.
+__device__ __forceinline__ void transpose8x8(uint32_t (&a)[8], int lane) {
+#pragma unroll
+  for (int d = 4; d >= 1; d >>= 1) {
+    const bool up = (lane & d) != 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k & d) continue;
+      const uint32_t send = up ? a[k] : a[k | d];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, d);
+      if (up) a[k] = recv; else a[k | d] = recv;
+    }
+  }
 }
 
 }  // namespace umma
