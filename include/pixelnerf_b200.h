@@ -168,6 +168,11 @@ int pnr_ingest_bench_tma(const void* src, int src_stages, int n_stages, int dept
 int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid, long long* out, int commit_every,
                    void* stream);
 
+/* Design-aid micro-benchmark: distributed-shared-memory ping-pong of `bytes` between the two CTAs of a cluster.
+ * mode 0: st.shared::cluster.v4 by `warps` warps + proxy fence + remote arrive; mode 1: one cp.async.bulk smem->peer smem.
+ * out[2] = elapsed SM cycles per CTA for `iters` one-way transfers. */
+int pnr_dsmem_bench(int mode, int bytes, int iters, int warps, long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ EXPORTS = [
     "pnr_sample_fine", "pnr_pack_features", "pnr_gather_encode", "pnr_mlp_pack_bytes", "pnr_mlp_pack",
     "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_umma_selftest",
     "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
-    "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench",
+    "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench",
 ]
 
 
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.pnr_ingest_bench.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]
     lib.pnr_ingest_bench_tma.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.pnr_umma_bench.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp]
+    lib.pnr_dsmem_bench.argtypes = [i32, i32, i32, i32, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)          # AttributeError here = header and library disagree
     if lib.pnr_version() != 1:
