@@ -132,7 +132,8 @@ int pnr_mlp_pack(const pnr_mlp_params* p, void* packed, void* stream);
 /* ---- field function: PixelNeRFNet.forward (src/model/models.py:153-318) -------------------------- */
 /* out (SB*P, 4) fp32 = [sigmoid(rgb), relu(sigma)].  precision PNR_PREC_FP32 uses `params` and a
  * caller workspace of pnr_field_workspace_bytes(); PNR_PREC_BF16 uses `packed` (from pnr_mlp_pack)
- * and needs no workspace. */
+ * and a small caller workspace (pnr_field_workspace_bytes(): 256 KiB of view-mean scratch per SM pair,
+ * 16-byte aligned; its contents need not survive the call but two concurrent calls need two workspaces). */
 size_t pnr_field_workspace_bytes(const pnr_scene* scene, const pnr_points* pts, int precision);
 int pnr_field_forward(const pnr_scene* scene, const pnr_points* pts, const pnr_mlp_params* params,
                       const void* packed, float* out, void* workspace, size_t workspace_bytes,

@@ -19,8 +19,10 @@ int validate_scene_points(const pnr_scene* sc, const pnr_points* q, const char* 
 size_t field_workspace_fp32(const pnr_scene* sc, const pnr_points* q, int d_in, int H);
 int field_forward_fp32(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, float* out, void* ws,
                        size_t ws_bytes, int num_freqs, float freq_factor, int raw, cudaStream_t st);
+size_t field_workspace_umma();
 int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const void* packed,
-                       float* out, int num_freqs, float freq_factor, int raw, cudaStream_t st);
+                       float* out, void* ws, size_t ws_bytes, int num_freqs, float freq_factor, int raw,
+                       cudaStream_t st);
 }  // namespace pnr
 
 using namespace pnr;
@@ -42,6 +44,7 @@ extern "C" int pnr_device_supported(void) {
 extern "C" size_t pnr_field_workspace_bytes(const pnr_scene* scene, const pnr_points* pts, int precision) {
   if (!scene || !pts) return 0;
   if (precision == PNR_PREC_FP32) return field_workspace_fp32(scene, pts, 64, kHidden);
+  if (precision == PNR_PREC_BF16) return field_workspace_umma();
   return 0;
 }
 
@@ -58,6 +61,6 @@ extern "C" int pnr_field_forward(const pnr_scene* scene, const pnr_points* pts, 
     return field_forward_fp32(scene, pts, params, out, workspace, workspace_bytes, num_freqs, freq_factor, 0, st);
   }
   if (precision == PNR_PREC_BF16)
-    return field_forward_umma(scene, pts, params, packed, out, num_freqs, freq_factor, 0, st);
+    return field_forward_umma(scene, pts, params, packed, out, workspace, workspace_bytes, num_freqs, freq_factor, 0, st);
   PNR_REQUIRE(false, PNR_ERR_ARG, "pnr_field_forward: unknown precision %d", precision);
 }

@@ -119,9 +119,10 @@ __host__ __device__ inline StageSrc decode_stage(const Sched& sc, int s) {
 // CTA-pair kernel (mlp_umma_pair.cu)
 size_t pair_stream_bytes(const pnr_mlp_params* p);
 int pair_pack(const pnr_mlp_params* p, uint8_t* stream, cudaStream_t st);
+size_t pair_workspace_bytes();
 int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const uint8_t* stream,
-                       const float* bx, const float* bh, const float* bo, float* out, int num_freqs, float freq_factor,
-                       int raw, cudaStream_t st);
+                       const float* bx, const float* bh, const float* bo, float* out, void* ws, size_t ws_bytes,
+                       int num_freqs, float freq_factor, int raw, cudaStream_t st);
 
 struct PackOffsets { size_t stages, bias_x, bias_h, bias_out, pair_stream, total; };
 static PackOffsets pack_offsets(const Sched& s, const pnr_mlp_params* p) {
@@ -725,8 +726,11 @@ static int cluster_size_setting() {
   return cached;
 }
 
+size_t field_workspace_umma() { return use_pair_kernel() ? pair_workspace_bytes() : 0; }
+
 int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const void* packed,
-                       float* out, int num_freqs, float freq_factor, int raw, cudaStream_t st) {
+                       float* out, void* ws, size_t ws_bytes, int num_freqs, float freq_factor, int raw,
+                       cudaStream_t st) {
   Sched sch;
   int rc = make_sched(mp, &sch, "field_forward_umma");
   if (rc) return rc;
@@ -760,7 +764,7 @@ int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   const float* bh = (const float*)(blob + po.bias_h);
   const float* bo = (const float*)(blob + po.bias_out);
   if (use_pair_kernel())
-    return field_forward_pair(sc, q, mp, blob + po.pair_stream, bx, bh, bo, out, num_freqs, freq_factor, raw, st);
+    return field_forward_pair(sc, q, mp, blob + po.pair_stream, bx, bh, bo, out, ws, ws_bytes, num_freqs, freq_factor, raw, st);
 #define PNR_LAUNCH_NS(NSV)                                                                                   \
   case NSV: {                                                                                                \
     auto kern = field_umma_kernel<NSV>;                                                                      \

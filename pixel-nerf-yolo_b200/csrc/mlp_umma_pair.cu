@@ -54,6 +54,8 @@ __host__ __device__ inline int z_passes(const Sched& s) { return (s.KBz + 7) / 8
 __host__ __device__ inline int sched_total(const Sched& s) {
   return kMT + s.n_linz * kMT * s.KBz + s.n_blocks * 32 + kKBlocksH;
 }
+// stages [0, sched_pre) are the pre-combine part (run once per tile), the rest the post-combine part
+__host__ __device__ inline int sched_pre(const Sched& s) { return kMT + s.n_linz * kMT * s.KBz + s.CL * 32; }
 // per-tile stage order = MMA issue order:
 //   lin_in (2) | lin_z[0] | per block: fc_0 (K-chunk outer: kc(4) x mt(2) x kk(2)) | lin_z[b+1] | fc_1 (same) | lin_out (8)
 __host__ __device__ inline Seg walk_stage(const Sched& sc, int s) {
@@ -133,7 +135,7 @@ struct Smem {
 };
 enum {
   B_W_FULL = 0, B_W_EMPTY = B_W_FULL + kStages, B_IN_READY = B_W_EMPTY + kStages, B_IN_FREE, B_X_FULL, B_H_FULL,
-  B_RDY, B_COUNT = B_RDY + 4
+  B_RDY, B_X_FREE = B_RDY + 4, B_COUNT
 };
 static_assert(B_COUNT <= 30, "barrier parity bits live in one 32-bit word");
 static_assert(Smem::total <= 227 * 1024, "shared memory budget");
@@ -230,18 +232,27 @@ __device__ long long* g_prof_pair = nullptr;
 #define PPROF_T0() const long long t0__ = prof ? clock64() : 0
 #define PPROF_ADD(slot) do { if (prof && lane == 0) prof[slot] += clock64() - t0__; } while (0)
 
+// Work unit of a CTA pair = a "super group": G = 64 / PP consecutive tile pairs.
+//   pre-combine  (G times): tile of PP points x NS views per CTA: gather, lin_in, lin_z, blocks [0, CL), view mean
+//                -> x-bar (fp32, bias folded in) into this pair's private scratch (L2-resident, 256 KiB per pair);
+//   post-combine (once)   : the G x PP (<= 64) points each CTA gathered form ONE 64-column tile: x-bar -> TMEM,
+//                blocks [CL, n_blocks), lin_out, sigmoid/relu.
+// So every MMA of the kernel runs at N = 128, and the post-combine layers need 1/G of the weight passes and
+// epilogue hand-offs per point that a per-tile post phase would.
 template <int NS>
 __global__ void __launch_bounds__(kThreads, 1)
 field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant__ CUtensorMap wmap,
                   const float* __restrict__ bias_x, const float* __restrict__ bias_h,
-                  const float* __restrict__ bias_out, float* __restrict__ out, const Sched sch, const int num_freqs,
-                  const float freq_factor, const int tiles_per_obj, const int n_tiles, const int d_out,
-                  const int raw_out) {
+                  const float* __restrict__ bias_out, float* __restrict__ out, float* __restrict__ xbar_all,
+                  const Sched sch, const int num_freqs, const float freq_factor, const int tiles_per_obj,
+                  const int n_tiles, const int d_out, const int raw_out) {
   const uint32_t crank = cluster_ctarank();            // 0 = leader (issues every MMA of the pair)
-  const int n_groups = (n_tiles + 1) / 2;              // one tile per CTA of the pair
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  constexpr int PP = kNCol / NS;
-  constexpr int NPOST = ((PP + 15) / 16) * 16;         // operand rows per CTA after the view mean
+  constexpr int PP = kNCol / NS;                       // points per pre-combine tile
+  constexpr int G = kNCol / PP;                        // pre-combine tile pairs per super group
+  constexpr int NLIVE = G * PP;                        // live columns of a post-combine tile (<= 64)
+  const int n_sg = ((n_tiles + 1) / 2 + G - 1) / G;
+  float* const xbar = xbar_all + (size_t)pair_id * (2 * kNCol * kHidden);   // [tile slot 2][column 64][feature 512]
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   volatile uint32_t* tmem_base_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::bars + 8 * B_COUNT);
@@ -260,13 +271,16 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     mbar_init(bar(B_X_FULL), 1);
     mbar_init(bar(B_H_FULL), 1);
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_RDY + i), kEpiWarps);
+    mbar_init(bar(B_X_FREE), 2 * kEpiWarps);
     fence_barrier_init();
   }
   const int n_stages = sched_total(sch);
+  const int s_pre = sched_pre(sch);                 // stages [0, s_pre) run per pre-combine tile, [s_pre, n_stages) per super group
+  const int n_flat = G * s_pre + (n_stages - s_pre);   // weight stages one super group consumes
   for (int i = threadIdx.x; i < n_stages; i += kThreads) {
     ProgEntry pe = make_prog(sch, i, sbase);
     int run = 1;
-    while (run < 8 && i + run < n_stages && (make_prog(sch, i + run, sbase).w0 >> 25) == 0) ++run;
+    while (run < 8 && i + run < n_stages && i + run != s_pre && (make_prog(sch, i + run, sbase).w0 >> 25) == 0) ++run;
     pe.w1 |= (uint32_t)run << 10;
     reinterpret_cast<ProgEntry*>(smem + Smem::prog)[i] = pe;
   }
@@ -276,17 +290,18 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
   cluster_sync_all();                    // both CTAs' barriers initialised and TMEM allocated before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
-  const uint32_t idesc_pre = instr_desc_bf16_2sm(2 * kNCol), idesc_post = instr_desc_bf16_2sm(2 * NPOST);
+  const uint32_t idesc = instr_desc_bf16_2sm(2 * kNCol);
 
   if (warp == 0 || warp == 12 || warp == 13) {
     // ===================== weight producers: warp p streams global stages g = p (mod kProducers); each CTA loads its
     // 128-row half of every 256-row slab, both halves complete on the LEADER's W_FULL barrier
     const int pid = warp == 0 ? 0 : warp - 11;
     uint32_t slot = pid, par = 1;
-    int carry = pid;                                    // first stage of this producer inside the current tile
-    for (int grp = pair_id; grp < n_groups; grp += n_pairs) {
-      int st = carry;
-      for (; st < n_stages; st += kProducers) {
+    int carry = pid;                                    // first stage of this producer inside the current super group
+    for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
+      int fi = carry;
+      for (; fi < n_flat; fi += kProducers) {
+        const int st = fi < G * s_pre ? fi % s_pre : fi - (G - 1) * s_pre;   // G passes over the pre stages, one over the post stages
         mbar_wait_cluster(bar(B_W_EMPTY + slot), par);
         if (elect_one()) {
           if (crank == 0) mbar_arrive_expect_tx(bar(B_W_FULL + slot), 2 * kStageBytes);
@@ -296,7 +311,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         slot += kProducers;
         if (slot >= kStages) { slot -= kStages; par ^= 1; }
       }
-      carry = st - n_stages;                            // the ring position continues across tiles
+      carry = fi - n_flat;                              // the ring position continues across super groups
     }
   } else if (warp == 1) {
     if (crank == 0) {
@@ -307,8 +322,18 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       const uint64_t bdesc_hi = smem_desc(0);
       constexpr uint64_t kStageStep = kStageBytes >> 4;
       const uint2* prog = reinterpret_cast<const uint2*>(smem + Smem::prog);
-      for (int grp = pair_id; grp < n_groups; grp += n_pairs) {
-        for (int st = 0; st < n_stages;) {
+      for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
+       for (int seg = 0; seg <= G; ++seg) {              // G pre-combine passes, then the post-combine pass
+        if (seg > 0 && seg < G) {
+          // the view-mean epilogue of the previous tile must have read x out of TMEM before lin_in overwrites it
+          PPROF_T0();
+          mbar_wait_cluster(bar(B_X_FREE), (ph >> B_X_FREE) & 1u);
+          ph ^= (1u << B_X_FREE);
+          tc_fence_after();
+          PPROF_ADD(5);
+        }
+        const int st_end = seg < G ? s_pre : n_stages;
+        for (int st = seg < G ? 0 : s_pre; st < st_end;) {
           const uint2 cur = prog[st];
           const uint32_t wait_id = cur.x >> 25;
           if (wait_id) {
@@ -341,7 +366,6 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               if (r + 1 < batch) en = prog[st + r + 1];
               const uint64_t b_desc = bdesc_hi | (uint64_t)(ecur.x & 0x3FFFu);
               const uint32_t d_col = (ecur.x >> 14) & 0x1FFu;
-              const uint32_t idesc = (ecur.x & (1u << 24)) ? idesc_post : idesc_pre;
               mma_kblock_desc_2sm(tmem_base + d_col, wdesc0 + sl * kStageStep, b_desc, idesc, (ecur.x >> 23) & 1u);
               mma_commit_2sm(bar(B_W_EMPTY + sl), 3);
               const uint32_t c1 = ecur.y & 31u, c2 = (ecur.y >> 5) & 31u;
@@ -357,6 +381,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           slot += batch;
           if (slot >= kStages) { slot -= kStages; wpar ^= 1; }
         }
+       }
       }
       if (prof && lane == 0) prof[0] += clock64() - t_role0;
     }
@@ -389,100 +414,121 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_RDY + kc)); else mbar_arrive_cluster_relaxed(lbar(B_RDY + kc)); }
       if (prof && prof_warp && lane == 0) prof[18] += clock64() - tp0;
     };
-    // both halves of a unit: columns [part*NC/2 ...) of tile `peer` (remote rows) then of tile `crank` (local rows)
-    auto convert_unit = [&](uint32_t tcol, int nch, int kc, float bias, bool post) {
+    // both halves of a unit: columns [hs*32, hs*32+32) of tile `peer` (remote rows) then of tile `crank` (local rows)
+    auto convert_unit = [&](uint32_t tcol, int kc, float bias) {
       const uint32_t loc = sbase + Smem::ring + kc * kChunkBytes;
       const uint32_t rem = mapa_u32(loc, peer);
-      if (!post) {
-        uint32_t v[kNCol / 2];
-        tmem_ld<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);
-        store_transposed<kNCol / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (kNCol / 2));
-        tmem_ld<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), v);
-        store_transposed<kNCol / 2, false, true>(loc, v, bias, lane, qd * 32, hs * (kNCol / 2));
-      } else if constexpr (NPOST >= 32) {
-        uint32_t v[NPOST / 2];
-        tmem_ld<NPOST / 2>(tlane + tcol + peer * NPOST + hs * (NPOST / 2), v);
-        store_transposed<NPOST / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (NPOST / 2));
-        tmem_ld<NPOST / 2>(tlane + tcol + crank * NPOST + hs * (NPOST / 2), v);
-        store_transposed<NPOST / 2, false, true>(loc, v, bias, lane, qd * 32, hs * (NPOST / 2));
-      } else if (hs == 0) {      // 16 post-combine columns per tile: too few to split, warp (qd,0) converts both tiles
-        uint32_t v[NPOST];
-        tmem_ld<NPOST>(tlane + tcol + peer * NPOST, v);
-        store_transposed<NPOST, true, true>(rem, v, bias, lane, qd * 32, 0);
-        tmem_ld<NPOST>(tlane + tcol + crank * NPOST, v);
-        store_transposed<NPOST, false, true>(loc, v, bias, lane, qd * 32, 0);
-      }
-      (void)nch;
+      uint32_t v[kNCol / 2];
+      tmem_ld<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);
+      store_transposed<kNCol / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (kNCol / 2));
+      tmem_ld<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), v);
+      store_transposed<kNCol / 2, false, true>(loc, v, bias, lane, qd * 32, hs * (kNCol / 2));
     };
-    for (int grp = pair_id; grp < n_groups; grp += n_pairs) {
-      const int tile = grp * 2 + hs;               // mean / output epilogues: the tile whose columns this warp handles
-      const bool live = tile < n_tiles;
-      const int obj = tile / tiles_per_obj;
-      const int p0 = (tile - obj * tiles_per_obj) * PP;
-      for (int e = 0; e <= sch.n_blocks; ++e) {
+    auto x_epilogue = [&](int e) {                 // relu(x + cumulative bias) -> bf16 K-chunks
+      wait(B_X_FULL);
+      for (int mt = 0; mt < kMT; ++mt) {
+        const int kc = 2 * mt + (int)crank;
+        const float bias = bias_x[e * kHidden + mt * 256 + crank * 128 + fl];
+        const long long ts0 = (prof && prof_warp) ? clock64() : 0;
+        convert_unit(mt * 128, kc, bias);
+        if (prof && prof_warp && lane == 0) prof[14] += clock64() - ts0;
+        publish(kc);
+      }
+    };
+    auto h_epilogue = [&](int b) {                 // relu(fc_0 out + b) -> bf16 K-chunks for fc_1
+      wait(B_H_FULL);
+      for (int mt = 0; mt < kMT; ++mt) {
+        const int kc = 2 * mt + (int)crank;
+        const float bias = bias_h[b * kHidden + mt * 256 + crank * 128 + fl];
+        convert_unit(kHCol + mt * 128, kc, bias);
+        publish(kc);
+      }
+    };
+    for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
+      // ================= pre-combine: G tile pairs; warp (qd, hs) takes the view mean of tile hs of each pair
+      for (int g = 0; g < G; ++g) {
+        const int tile = (sg * G + g) * 2 + hs;
+        const bool live = tile < n_tiles;
+        const int obj = tile / tiles_per_obj;
+        const int p0 = (tile - obj * tiles_per_obj) * PP;
+        for (int e = 0; e < sch.CL; ++e) { x_epilogue(e); h_epilogue(e); }
         wait(B_X_FULL);
+        // view mean (combine_interleaved) + cumulative bias -> x-bar, column g*PP + p of slot hs
         for (int mt = 0; mt < kMT; ++mt) {
-          const int kc = 2 * mt + (int)crank;
-          const float bias = bias_x[e * kHidden + mt * 256 + crank * 128 + fl];
-          if (e != sch.CL) {
-            const long long ts0 = (prof && prof_warp) ? clock64() : 0;
-            convert_unit(mt * 128, 0, kc, bias, e > sch.CL);
-            if (prof && prof_warp && lane == 0) prof[14] += clock64() - ts0;
-          } else {
-            // view mean (combine_interleaved): warp (qd, hs) owns tile hs
-            const bool remote = (uint32_t)hs != crank;
-            uint32_t m[NPOST];
-            {
-              uint32_t v[kNCol];
-              tmem_ld<kNCol>(tlane + mt * 128 + hs * kNCol, v);
-              // the post-combine layout packs NPOST columns per CTA: warp (qd,1) writes columns that warp (qd,0) reads
-              asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+          const int f = mt * 256 + (int)crank * 128 + fl;
+          const float bias = bias_x[sch.CL * kHidden + f];
+          uint32_t v[kNCol];
+          tmem_ld<kNCol>(tlane + mt * 128 + hs * kNCol, v);
+          float* dst = xbar + ((size_t)hs * kNCol + g * PP) * kHidden + f;
 #pragma unroll
-              for (int p = 0; p < NPOST; ++p) {
-                float acc = 0.f;
-                if (p < PP) {
+          for (int p = 0; p < PP; ++p) {
+            float acc = 0.f;
 #pragma unroll
-                  for (int vw = 0; vw < NS; ++vw) acc += __uint_as_float(v[vw * PP + p]);
-                  acc = __fdiv_rn(acc, (float)NS) + bias;
-                }
-                m[p] = __float_as_uint(acc);
-              }
-            }
-            tmem_st<NPOST>(tlane + mt * 128 + hs * NPOST, m);      // x-bar (bias included), post-combine column layout
-            const uint32_t loc = sbase + Smem::ring + kc * kChunkBytes;
-            if (remote) store_transposed<NPOST, true, false>(mapa_u32(loc, (uint32_t)hs), m, 0.f, lane, qd * 32, 0);
-            else store_transposed<NPOST, false, false>(loc, m, 0.f, lane, qd * 32, 0);
-          }
-          publish(kc);
-        }
-        if (e < sch.n_blocks) {
-          wait(B_H_FULL);
-          for (int mt = 0; mt < kMT; ++mt) {
-            const int kc = 2 * mt + (int)crank;
-            const float bias = bias_h[e * kHidden + mt * 256 + crank * 128 + fl];
-            convert_unit(kHCol + mt * 128, 0, kc, bias, e >= sch.CL);
-            publish(kc);
+            for (int vw = 0; vw < NS; ++vw) acc += __uint_as_float(v[vw * PP + p]);
+            const bool ok = live && p0 + p < q.P;
+            __stcg(dst + (size_t)p * kHidden, ok ? __fdiv_rn(acc, (float)NS) + bias : 0.f);
           }
         }
+        if (g + 1 < G) {                            // TMEM reads done -> the next tile's lin_in may overwrite x
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_X_FREE)); else mbar_arrive_cluster_relaxed(lbar(B_X_FREE)); }
+        }
+      }
+      // ================= post-combine: one tile of 64 columns per CTA (column j = g*PP + p of the tiles above)
+      // warp (qd, 1-hs) wrote the x-bar values this warp loads and read the TMEM columns it overwrites
+      tc_fence_before();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      tc_fence_after();
+      for (int mt = 0; mt < kMT; ++mt) {
+        const int kc = 2 * mt + (int)crank;
+        const int f = mt * 256 + (int)crank * 128 + fl;
+        const uint32_t loc = sbase + Smem::ring + kc * kChunkBytes;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t t = half == 0 ? peer : crank;            // peer's columns first (remote rows)
+          const float* src = xbar + ((size_t)t * kNCol + hs * (kNCol / 2)) * kHidden + f;
+          uint32_t v[kNCol / 2];
+#pragma unroll
+          for (int c = 0; c < kNCol / 2; ++c)
+            v[c] = (hs * (kNCol / 2) + c < NLIVE) ? __float_as_uint(__ldcg(src + (size_t)c * kHidden)) : 0u;
+          tmem_st<kNCol / 2>(tlane + mt * 128 + t * kNCol + hs * (kNCol / 2), v);
+          if (half == 0) store_transposed<kNCol / 2, true, false>(mapa_u32(loc, peer), v, 0.f, lane, qd * 32, hs * (kNCol / 2));
+          else store_transposed<kNCol / 2, false, false>(loc, v, 0.f, lane, qd * 32, hs * (kNCol / 2));
+        }
+        publish(kc);
+      }
+      h_epilogue(sch.CL);
+      for (int e = sch.CL + 1; e <= sch.n_blocks; ++e) {
+        x_epilogue(e);
+        if (e < sch.n_blocks) h_epilogue(e);
       }
       // ---- output: lin_out rows are features 0..d_out-1 -> leader CTA, TMEM lanes 0..d_out-1 of h tile 0
       wait(B_H_FULL);
-      {
-        uint32_t r[NPOST];
-        tmem_ld<NPOST>(tlane + kHCol + hs * NPOST, r);
-        tc_fence_before();
-        if (crank == 0 && live && qd == 0 && lane < d_out) {
+      if (crank == 0 && qd == 0) {
+        uint32_t r[kNCol];
+        tmem_ld<kNCol>(tlane + kHCol + hs * kNCol, r);
+        if (lane < d_out) {
           const float bias = bias_out[lane];
 #pragma unroll
-          for (int p = 0; p < PP; ++p) {
-            if (p0 + p < q.P) {
-              float val = __uint_as_float(r[p]) + bias;
-              if (!raw_out) val = lane < 3 ? 1.0f / (1.0f + expf(-val)) : fmaxf(val, 0.f);   // models.py:312-317
-              out[((size_t)obj * q.P + p0 + p) * d_out + lane] = val;
+          for (int g = 0; g < G; ++g) {
+            const int tile = (sg * G + g) * 2 + hs;
+            const int obj = tile / tiles_per_obj;
+            const int p0 = (tile - obj * tiles_per_obj) * PP;
+            if (tile < n_tiles) {
+#pragma unroll
+              for (int p = 0; p < PP; ++p) {
+                if (p0 + p < q.P) {
+                  float val = __uint_as_float(r[g * PP + p]) + bias;
+                  if (!raw_out) val = lane < 3 ? 1.0f / (1.0f + expf(-val)) : fmaxf(val, 0.f);   // models.py:312-317
+                  out[((size_t)obj * q.P + p0 + p) * d_out + lane] = val;
+                }
+              }
             }
           }
         }
       }
+      tc_fence_before();
     }
     if (prof && prof_warp && lane == 0) prof[8] += clock64() - t_role0;
   } else if (warp == 2 || warp == 3 || warp == 14 || warp == 15) {
@@ -492,10 +538,49 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     const long long t_role0 = prof ? clock64() : 0;
     const int n_pass = z_passes(sch);
     const int fills = n_pass > 1 ? sch.n_linz * n_pass : 1;
-    for (int grp = pair_id; grp < n_groups; grp += n_pairs) {
-      const int tile = grp * 2 + (int)crank;
+    for (int it = 0;; ++it) {                        // tile pairs sg*G + g of super groups sg = pair_id, pair_id + n_pairs, ...
+      const int sg = pair_id + (it / G) * n_pairs;
+      if (sg >= n_sg) break;
+      const int tile = (sg * G + it % G) * 2 + (int)crank;
       const int obj = tile / tiles_per_obj;
       const int p0 = (tile - obj * tiles_per_obj) * PP;
+      // ---- pre-pass, before the operand buffers are free (touches no shared memory): this warp owns columns
+      // c_i = gw + 4 i (i < 16); lane i (and i + 16) projects column c_i, then every lane computes its two
+      // z-feature elements of all 16 columns
+      Taps tp;
+      long long vbase = -1;                          // element offset of this lane's column's source view, -1 = dead column
+      Projection pr;
+      {
+        const int c = gw + kGatherWarps * (lane & 15);
+        const int v = c / PP, p = c - v * PP;
+        const bool valid = (tile < n_tiles) && (v < NS) && (p0 + p < q.P);
+        pr.xr = pr.yr = pr.zr = pr.dx = pr.dy = pr.dz = pr.ix = pr.iy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tp.off[k] = -1; tp.w[k] = 0.f; }
+        if (valid) {
+          float px, py, pz, vx, vy, vz;
+          const int view = obj * NS + v;
+          fetch_point(q, (long long)obj * q.P + p0 + p, px, py, pz, vx, vy, vz);
+          pr = project_point(sc, view, px, py, pz, vx, vy, vz);
+          tp = make_taps(pr.ix, pr.iy, sc.Hl, sc.Wl, sc.C);
+          vbase = (long long)view * sc.Hl * sc.Wl * sc.C;
+        }
+      }
+      auto zfeat_col = [&](int i) {                  // z-feature row of column c_i: every lane computes two elements
+        Projection pi;
+        pi.xr = __shfl_sync(0xffffffffu, pr.xr, i); pi.yr = __shfl_sync(0xffffffffu, pr.yr, i);
+        pi.zr = __shfl_sync(0xffffffffu, pr.zr, i); pi.dx = __shfl_sync(0xffffffffu, pr.dx, i);
+        pi.dy = __shfl_sync(0xffffffffu, pr.dy, i); pi.dz = __shfl_sync(0xffffffffu, pr.dz, i);
+        pi.ix = pi.iy = 0.f;
+        const bool vi = __shfl_sync(0xffffffffu, vbase, i) >= 0;
+        const int j0 = lane * 2, d_in = 6 * num_freqs + 6;
+        float a = 0.f, b = 0.f;
+        if (vi) {
+          if (j0 < d_in) a = zfeat_value(pi, j0, num_freqs, freq_factor);
+          if (j0 + 1 < d_in) b = zfeat_value(pi, j0 + 1, num_freqs, freq_factor);
+        }
+        *reinterpret_cast<__nv_bfloat162*>(smem + Smem::zf + swz_offset(gw + kGatherWarps * i, j0)) = __floats2bfloat162_rn(a, b);
+      };
       for (int fill = 0; fill < fills; ++fill) {
         const int pass = fill % n_pass;
         const int kp = sch.KBz - pass * 8 < 8 ? sch.KBz - pass * 8 : 8;
@@ -506,61 +591,66 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           if (gw == 0) PPROF_ADD(17);
         }
         par_free ^= 1;
-        for (int c = gw; c < kNCol; c += kGatherWarps) {
-          const int v = c / PP, p = c - v * PP;
-          const bool valid = (tile < n_tiles) && (v < NS) && (p0 + p < q.P);
-          Projection pr;
-          Taps tp;
-          const int view = obj * NS + (v < NS ? v : 0);
-          if (valid) {
-            float px, py, pz, vx, vy, vz;
-            fetch_point(q, (long long)obj * q.P + p0 + p, px, py, pz, vx, vy, vz);
-            pr = project_point(sc, view, px, py, pz, vx, vy, vz);
-            tp = make_taps(pr.ix, pr.iy, sc.Hl, sc.Wl, sc.C);
+        // ---- 4 taps x 1 KiB per column, two columns in flight per warp (the loads are L2 hits with ~1-2 k cycles of
+        // latency under the weight stream's load; one column at a time left the tensor cores waiting for the gather)
+        const bool act = (lane >> 2) < kp;
+        const __nv_bfloat16* fl0 = (const __nv_bfloat16*)sc.feat + ch0 + lane * 16;
+        auto load_col = [&](int i, uint4 (&r)[8], float (&w)[4]) {
+          const long long vb = __shfl_sync(0xffffffffu, vbase, i);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int off = __shfl_sync(0xffffffffu, tp.off[k], i);
+            w[k] = __shfl_sync(0xffffffffu, tp.w[k], i);
+            if (off >= 0 && act) {
+              const uint4* src = reinterpret_cast<const uint4*>(fl0 + vb + off);
+              r[2 * k] = __ldg(src); r[2 * k + 1] = __ldg(src + 1);
+            } else {
+              r[2 * k] = make_uint4(0u, 0u, 0u, 0u); r[2 * k + 1] = make_uint4(0u, 0u, 0u, 0u);
+            }
           }
-          if (fill == 0) {
-            const int j0 = lane * 2;
-            float a = 0.f, b = 0.f;
-            const int d_in = 6 * num_freqs + 6;
-            if (valid) {
-              if (j0 < d_in) a = zfeat_value(pr, j0, num_freqs, freq_factor);
-              if (j0 + 1 < d_in) b = zfeat_value(pr, j0 + 1, num_freqs, freq_factor);
+        };
+        auto blend_col = [&](int i, const uint4 (&r)[8], const float (&w)[4]) {
+          if (!act) return;
+          float acc[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r[2 * k]);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r[2 * k + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+              acc[2 * j] += w[k] * f0.x; acc[2 * j + 1] += w[k] * f0.y;
+              acc[8 + 2 * j] += w[k] * f1.x; acc[8 + 2 * j + 1] += w[k] * f1.y;
             }
-            *reinterpret_cast<__nv_bfloat162*>(smem + Smem::zf + swz_offset(c, j0)) = __floats2bfloat162_rn(a, b);
           }
-          if ((lane >> 2) < kp) {
-            float acc[16];
+          uint4 o0, o1;
+          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-            if (valid) {
-              const __nv_bfloat16* fmap = (const __nv_bfloat16*)sc.feat + (size_t)view * sc.Hl * sc.Wl * sc.C + ch0 + lane * 16;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (tp.off[k] < 0) continue;
-                const uint4* src = reinterpret_cast<const uint4*>(fmap + tp.off[k]);
-                const uint4 r0 = __ldg(src), r1 = __ldg(src + 1);
-                const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-                const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float2 f0 = __bfloat1622float2(h0[i]), f1 = __bfloat1622float2(h1[i]);
-                  acc[2 * i] += tp.w[k] * f0.x; acc[2 * i + 1] += tp.w[k] * f0.y;
-                  acc[8 + 2 * i] += tp.w[k] * f1.x; acc[8 + 2 * i + 1] += tp.w[k] * f1.y;
-                }
-              }
-            }
-            uint4 o0, o1;
-            __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-            __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              q0[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-              q1[i] = __floats2bfloat162_rn(acc[8 + 2 * i], acc[8 + 2 * i + 1]);
-            }
-            uint8_t* kb_base = smem + Smem::lat + (lane >> 2) * kOperandKB;
-            const int k_in = (lane & 3) * 16;
-            *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in)) = o0;
-            *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in + 8)) = o1;
+          for (int j = 0; j < 4; ++j) {
+            q0[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            q1[j] = __floats2bfloat162_rn(acc[8 + 2 * j], acc[8 + 2 * j + 1]);
+          }
+          const int c = gw + kGatherWarps * i;
+          uint8_t* kb_base = smem + Smem::lat + (lane >> 2) * kOperandKB;
+          const int k_in = (lane & 3) * 16;
+          *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in)) = o0;
+          *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in + 8)) = o1;
+        };
+        {
+          uint4 ra[8], rb[8];
+          float wa[4], wb[4];
+          load_col(0, ra, wa);
+#pragma unroll 1
+          for (int i = 0; i < 16; i += 2) {
+            load_col(i + 1, rb, wb);
+            if (fill == 0) zfeat_col(i);             // sin/cos work hides part of the load latency
+            blend_col(i, ra, wa);
+            if (i + 2 < 16) load_col(i + 2, ra, wa);
+            if (fill == 0) zfeat_col(i + 1);
+            blend_col(i + 1, rb, wb);
           }
         }
         fence_proxy_async();                 // the gather writes this CTA's own shared memory only
@@ -597,9 +687,21 @@ int pair_pack(const pnr_mlp_params* p, uint8_t* stream, cudaStream_t st) {
   return PNR_OK;
 }
 
+// scratch for the view means: 2 tiles x 64 columns x 512 features fp32 per resident CTA pair
+size_t pair_workspace_bytes() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (size_t)(sms / 2) * 2 * pair::kNCol * kHidden * sizeof(float);
+}
+
 int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const uint8_t* stream,
-                       const float* bx, const float* bh, const float* bo, float* out, int num_freqs, float freq_factor,
-                       int raw, cudaStream_t st) {
+                       const float* bx, const float* bh, const float* bo, float* out, void* ws, size_t ws_bytes,
+                       int num_freqs, float freq_factor, int raw, cudaStream_t st) {
+  PNR_REQUIRE(ws && ws_bytes >= pair_workspace_bytes() && ((uintptr_t)ws & 15) == 0, PNR_ERR_ARG,
+              "field_forward_pair: workspace of pnr_field_workspace_bytes() = %zu bytes required (got %zu)",
+              pair_workspace_bytes(), ws_bytes);
+  float* xbar = (float*)ws;
   pair::Sched sch{mp->n_blocks, mp->combine_layer, mp->combine_layer, mp->d_latent / 64};
   const int PP = pair::kNCol / sc->NS;
   const int tiles_per_obj = (q->P + PP - 1) / PP;
@@ -631,7 +733,8 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_groups = (n_tiles + 1) / 2;
+  const int G = pair::kNCol / PP;                        // tile pairs per super group (see field_pair_kernel)
+  const int n_groups = ((n_tiles + 1) / 2 + G - 1) / G;  // super groups
   long long* prof_dev = nullptr;
   if (getenv("PNR_PROF")) {
     cudaMalloc(&prof_dev, (size_t)4096 * 32 * sizeof(long long));
@@ -651,10 +754,10 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
     cfg.attrs = attr; cfg.numAttrs = 1;                                                                          \
     cfg.gridDim = dim3(sms / 2 * 2);                                                                             \
     int max_pairs = sms / 2, mc = 0;                                                                             \
-    if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) == cudaSuccess && mc > 0) max_pairs = mc;               \
+    if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) == cudaSuccess && mc > 0 && mc < max_pairs) max_pairs = mc; \
     const int n_pairs = n_groups < max_pairs ? n_groups : max_pairs;                                             \
     cfg.gridDim = dim3(n_pairs * 2);                                                                             \
-    e = cudaLaunchKernelEx(&cfg, kern, *sc, *q, tmap, bx, bh, bo, out, sch, num_freqs, freq_factor, tiles_per_obj, \
+    e = cudaLaunchKernelEx(&cfg, kern, *sc, *q, tmap, bx, bh, bo, out, xbar, sch, num_freqs, freq_factor, tiles_per_obj, \
                            n_tiles, (int)mp->d_out, raw);                                                        \
     PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "field_pair_kernel launch: %s", cudaGetErrorString(e));          \
   } break;
@@ -678,7 +781,7 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
       for (int k = 0; k < 32; ++k) sum[k] += (double)h[(size_t)b * 32 + k];
     }
     const double groups_per_pair = (double)n_groups / (leaders ? leaders : 1);
-    fprintf(stderr, "[pnr pair prof] tiles=%d pairs=%d tile-pairs/pair=%.1f  (cycles per tile-pair)\n", n_tiles, leaders, groups_per_pair);
+    fprintf(stderr, "[pnr pair prof] tiles=%d pairs=%d super-groups/pair=%.1f  (cycles per super group of %d tile pairs)\n", n_tiles, leaders, groups_per_pair, G);
     for (int k = 0; k < 32; ++k) if (names[k]) fprintf(stderr, "[pnr pair prof]   %-22s %10.0f\n", names[k], sum[k] / ((k < 8) ? (leaders ? leaders : 1) : (ctas ? ctas : 1)) / groups_per_pair);
     long long* null_ptr = nullptr;
     cudaMemcpyToSymbol(pair::g_prof_pair, &null_ptr, sizeof(null_ptr));

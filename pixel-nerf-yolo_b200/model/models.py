@@ -154,8 +154,10 @@ class PixelNeRFNet(torch.nn.Module):
         with torch.cuda.device(dev):
             if self.precision == "bf16":
                 sc, keep2 = self._scene(fp32_maps=False)
-                rc = lib.pnr_field_forward(sc, pts, mlp.c_params(), mlp.packed().data_ptr(), out.data_ptr(), None, 0,
-                                           _lib.PREC_BF16, self.code.num_freqs, self.code.freq_factor,
+                ws_bytes = lib.pnr_field_workspace_bytes(sc, pts, _lib.PREC_BF16)
+                ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)   # caching allocator: no cudaMalloc after the first call
+                rc = lib.pnr_field_forward(sc, pts, mlp.c_params(), mlp.packed().data_ptr(), out.data_ptr(),
+                                           ws.data_ptr(), ws_bytes, _lib.PREC_BF16, self.code.num_freqs, self.code.freq_factor,
                                            _lib.stream_ptr(dev))
                 _lib.check(rc, "pnr_field_forward(bf16)")
                 launches = lib.pnr_last_launch_count()
