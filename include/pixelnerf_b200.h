@@ -139,6 +139,42 @@ int pnr_field_forward(const pnr_scene* scene, const pnr_points* pts, const pnr_m
                       const void* packed, float* out, void* workspace, size_t workspace_bytes,
                       int precision, int num_freqs, float freq_factor, void* stream);
 
+/* ---- training step (BASELINE config 3): what loss.backward() does for the reference ------------------ */
+/* Gradient accumulators laid out like the pointer part of pnr_mlp_params: fp32 device buffers the backward pass ADDS into;
+ * the caller zeroes them, like optimizer.zero_grad(). */
+typedef struct pnr_mlp_grads {
+  float* lin_in_w;  float* lin_in_b;
+  float* lin_out_w; float* lin_out_b;
+  float* fc0_w[8];  float* fc0_b[8];
+  float* fc1_w[8];  float* fc1_b[8];
+  float* linz_w[8]; float* linz_b[8];
+} pnr_mlp_grads;
+
+/* PixelNeRFNet.forward in training mode: fp32 arithmetic, fp32 channels-last feature maps (feat_fp32=1), every
+ * activation the backward pass needs is kept on the caller-owned `tape` (pnr_field_tape_bytes()). */
+size_t pnr_field_tape_bytes(const pnr_scene* scene, const pnr_points* pts, const pnr_mlp_params* params);
+int pnr_field_forward_train(const pnr_scene* scene, const pnr_points* pts, const pnr_mlp_params* params, float* out,
+                            void* tape, size_t tape_bytes, int num_freqs, float freq_factor, void* stream);
+/* Backward of the call above.  out / d_out (SB*P, d_out): activated outputs and their gradient.  Adds the parameter
+ * gradients into `grads`; optionally adds into d_feat (fp32 channels-last, shape of scene->feat: the gradient that
+ * autograd sends into SpatialEncoder.latent through F.grid_sample, encoder.py:101-107) and into d_xyz (SB*P, 3;
+ * point mode 0) or d_z (SB*B*K; point mode 1, x = o + z d), which the caller zeroes.  Any of the three may be NULL. */
+size_t pnr_field_backward_workspace_bytes(const pnr_scene* scene, const pnr_points* pts, const pnr_mlp_params* params);
+int pnr_field_backward(const pnr_scene* scene, const pnr_points* pts, const pnr_mlp_params* params, const void* tape,
+                       const float* out, const float* d_out, const pnr_mlp_grads* grads, float* d_feat, float* d_xyz,
+                       float* d_z, void* workspace, size_t workspace_bytes, int num_freqs, float freq_factor,
+                       void* stream);
+/* Backward of pnr_composite (nerf.py:184-188, 229-255): d_rgb (B,3), d_depth (B, may be NULL), d_weights (B,K, may be
+ * NULL) -> d_rgb_sigma (B,K,4) and, if non-NULL, d_z (B,K) (both overwritten). */
+int pnr_composite_backward(const float* rgb_sigma, const float* z, const float* rays, const float* d_rgb,
+                           const float* d_depth, const float* d_weights, float* d_rgb_sigma, float* d_z, int B, int K,
+                           int white_bkgd, void* stream);
+/* Backward of sample_fine_depth + cat + sort (nerf.py:156-167, 296-301) with respect to the coarse depth:
+ * d_depth[b] = sum of d_z_sorted over the positions of the unclamped depth samples (overwritten). */
+int pnr_sample_fine_depth_backward(const float* z_sorted, const float* d_z_sorted, const float* depth,
+                                   const float* gauss, const float* rays, float* d_depth, int B, int K, int Kfd,
+                                   float depth_std, void* stream);
+
 /* ResnetFC.forward as a stand-alone operator (src/model/resnetfc.py:134-186), fp32 arithmetic.
  * zx (rows, d_latent + d_in) fp32, rows ordered (object, view, point) with NS views and P points per
  * object (combine_inner_dims = (NS, P)); out (rows / NS, d_out) raw lin_out values. */

@@ -136,6 +136,14 @@ def encode_cameras(latent: torch.Tensor, poses_c2w: torch.Tensor, focal: torch.T
 # --------------------------------------------------------------------------- #
 # ops
 # --------------------------------------------------------------------------- #
+def _f64(fn, x: torch.Tensor) -> torch.Tensor:
+    """Transcendental functions (sin, exp, sigmoid) are evaluated in double and rounded once to fp32.
+    ATen's fp32 CPU kernels are vectorised libm calls whose accuracy depends on the host's SIMD level (one GPU
+    box's host returned exp() values ~100 ulp off); the correctly rounded value is host-independent and within
+    1 ulp of what the reference's torch.sin / torch.exp / torch.sigmoid return on a healthy host."""
+    return fn(x.double()).to(x.dtype) if x.dtype == torch.float32 else fn(x)
+
+
 def positional_encoding(x: torch.Tensor, num_freqs: int = 6, freq_factor: float = 1.5,
                         include_input: bool = True) -> torch.Tensor:
     """code.py:11-42.  Layout: [x, sin(f0 x), cos(f0 x), sin(f1 x), ...] with cos as sin(.+pi/2)."""
@@ -145,7 +153,7 @@ def positional_encoding(x: torch.Tensor, num_freqs: int = 6, freq_factor: float 
     ph[1::2] = math.pi * 0.5                                                # code.py:26-27
     ph = ph.view(1, -1, 1)
     e = x.unsqueeze(1).repeat(1, num_freqs * 2, 1)
-    e = torch.sin(torch.addcmul(ph, e, f2))                                 # code.py:38
+    e = _f64(torch.sin, torch.addcmul(ph, e, f2))                           # code.py:38
     e = e.view(x.shape[0], -1)
     if include_input:
         e = torch.cat((x, e), dim=-1)
@@ -244,7 +252,7 @@ def field_forward(scene: Scene, mlp: Dict[str, torch.Tensor], xyz: torch.Tensor,
     out = out.reshape(-1, P, out.shape[-1])
     if return_raw:
         return out.reshape(SB, P, -1)
-    rgb = torch.sigmoid(out[..., :3])                                       # models.py:312-317
+    rgb = _f64(torch.sigmoid, out[..., :3])                                 # models.py:312-317
     sigma = torch.relu(out[..., 3:4])
     return torch.cat((rgb, sigma), dim=-1).reshape(SB, P, -1)
 
@@ -297,7 +305,7 @@ def alpha_composite(out: torch.Tensor, z: torch.Tensor, rays: torch.Tensor, whit
     deltas = z[:, 1:] - z[:, :-1]
     deltas = torch.cat([deltas, rays[:, -1:] - z[:, -1:]], -1)
     rgbs, sig = out[..., :3], out[..., 3]
-    alphas = 1 - torch.exp(-deltas * torch.relu(sig))
+    alphas = 1 - _f64(torch.exp, -deltas * torch.relu(sig))
     shifted = torch.cat([torch.ones_like(alphas[:, :1]), 1 - alphas + 1e-10], -1)
     T = torch.cumprod(shifted, -1)
     w = alphas * T[:, :-1]
@@ -320,13 +328,16 @@ def _composite(scene, mlp, rays, z, sb, white_bkgd, field_kw):
 def render(scene: Scene, mlp_coarse: Dict[str, torch.Tensor], mlp_fine: Optional[Dict[str, torch.Tensor]],
            rays: torch.Tensor, noise: RenderNoise, *, n_coarse: int = 64, n_fine: int = 32,
            n_fine_depth: int = 16, depth_std: float = 0.01, white_bkgd: bool = True,
-           lindisp: bool = False, **field_kw):
+           lindisp: bool = False, grad: bool = False, **field_kw):
     """NeRFRenderer.forward (nerf.py:257-309) with explicit noise.  rays (SB,B',8).
-    Returns dict(coarse=dict(rgb,depth,weights,z), fine=...)."""
+    Returns dict(coarse=dict(rgb,depth,weights,z), fine=...).  ``grad=True`` records the autograd graph exactly
+    as the reference's training step does (importance sampler on detached weights nerf.py:136,293; the depth
+    samples stay attached to the coarse depth nerf.py:296-298), so ``loss.backward()`` on the result gives the
+    gradients the CUDA backward kernels are checked against."""
     assert rays.dim() == 3
     SB = rays.shape[0]
     r = rays.reshape(-1, 8)
-    with torch.no_grad():
+    with torch.set_grad_enabled(grad):
         z_c = sample_coarse(r, noise.coarse, n_coarse, lindisp)
         wc, rgbc, dc = _composite(scene, mlp_coarse, r, z_c, SB, white_bkgd, field_kw)
         res = {"coarse": dict(rgb=rgbc.reshape(SB, -1, 3), depth=dc.reshape(SB, -1),
@@ -334,7 +345,7 @@ def render(scene: Scene, mlp_coarse: Dict[str, torch.Tensor], mlp_fine: Optional
         if n_fine > 0:
             parts = [z_c]
             if n_fine - n_fine_depth > 0:
-                parts.append(sample_fine(r, wc, noise.fine_u, noise.fine_jitter, n_coarse, lindisp))
+                parts.append(sample_fine(r, wc.detach(), noise.fine_u, noise.fine_jitter, n_coarse, lindisp))
             if n_fine_depth > 0:
                 parts.append(sample_fine_depth(r, dc, noise.depth, depth_std))
             z_all, _ = torch.sort(torch.cat(parts, dim=-1), dim=-1)         # nerf.py:300-301

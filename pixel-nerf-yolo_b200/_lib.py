@@ -25,6 +25,8 @@ EXPORTS = [
     "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_umma_selftest",
     "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
     "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench",
+    "pnr_field_tape_bytes", "pnr_field_forward_train", "pnr_field_backward_workspace_bytes", "pnr_field_backward",
+    "pnr_composite_backward", "pnr_sample_fine_depth_backward",
 ]
 
 
@@ -47,6 +49,14 @@ class MlpParams(C.Structure):
                 ("linz_b", C.c_void_p * 8), ("d_in", C.c_int32), ("d_latent", C.c_int32),
                 ("d_hidden", C.c_int32), ("d_out", C.c_int32), ("n_blocks", C.c_int32),
                 ("combine_layer", C.c_int32)]
+
+
+class MlpGrads(C.Structure):
+    """pnr_mlp_grads: fp32 accumulators laid out like MlpParams (without the dimensions)."""
+    _fields_ = [("lin_in_w", C.c_void_p), ("lin_in_b", C.c_void_p), ("lin_out_w", C.c_void_p),
+                ("lin_out_b", C.c_void_p), ("fc0_w", C.c_void_p * 8), ("fc0_b", C.c_void_p * 8),
+                ("fc1_w", C.c_void_p * 8), ("fc1_b", C.c_void_p * 8), ("linz_w", C.c_void_p * 8),
+                ("linz_b", C.c_void_p * 8)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -93,6 +103,16 @@ def load() -> C.CDLL:
     lib.pnr_ingest_bench_tma.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.pnr_umma_bench.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp]
     lib.pnr_dsmem_bench.argtypes = [i32, i32, i32, i32, vp, vp]
+    lib.pnr_field_tape_bytes.argtypes = [C.POINTER(Scene), C.POINTER(Points), C.POINTER(MlpParams)]
+    lib.pnr_field_tape_bytes.restype = C.c_size_t
+    lib.pnr_field_forward_train.argtypes = [C.POINTER(Scene), C.POINTER(Points), C.POINTER(MlpParams), vp, vp,
+                                            C.c_size_t, i32, f32, vp]
+    lib.pnr_field_backward_workspace_bytes.argtypes = [C.POINTER(Scene), C.POINTER(Points), C.POINTER(MlpParams)]
+    lib.pnr_field_backward_workspace_bytes.restype = C.c_size_t
+    lib.pnr_field_backward.argtypes = [C.POINTER(Scene), C.POINTER(Points), C.POINTER(MlpParams), vp, vp, vp,
+                                       C.POINTER(MlpGrads), vp, vp, vp, vp, C.c_size_t, i32, f32, vp]
+    lib.pnr_composite_backward.argtypes = [vp] * 8 + [i32, i32, i32, vp]
+    lib.pnr_sample_fine_depth_backward.argtypes = [vp] * 6 + [i32, i32, i32, f32, vp]
     for name in EXPORTS:
         getattr(lib, name)          # AttributeError here = header and library disagree
     if lib.pnr_version() != 1:

@@ -1,0 +1,543 @@
+// Training path of the field function: PixelNeRFNet.forward (src/model/models.py:153-318) with every activation
+// the backward pass needs kept on a caller-owned tape, and the backward pass itself -- gradients of all ResnetFC
+// parameters (src/model/resnetfc.py:103-132), of the encoder's feature maps (SpatialEncoder.latent, through the
+// bilinear gather, src/model/encoder.py:79-108) and of the query points (through the projection, models.py:168-230,
+// and the positional encoding, src/model/code.py:30-42; the renderer needs them because sample_fine_depth is
+// differentiable in the coarse depth, src/render/nerf.py:156-167,296-298).
+//
+// What autograd does for the reference (PixelNerfTrainer.calc_losses -> loss.backward(), BASELINE config 3) is one
+// explicit chain of kernels here.  Arithmetic is fp32 on the CUDA cores (SIMT SGEMM in all four operand layouts):
+// the training step is the parity case of this round (gradients vs autograd <= 1e-3 relative), not the timed one.
+#include "pnr_common.cuh"
+
+namespace pnr {
+
+int validate_scene_points(const pnr_scene* sc, const pnr_points* q, const char* who);
+
+namespace bwd {
+
+constexpr int BM = 128, BN = 128, BK = 8;
+
+struct GemmArgs {
+  const float* A; long long lda;     // A_T ? A[k*lda + i] : A[i*lda + k]
+  const float* B; long long ldb;     // B_T ? B[j*ldb + k] : B[k*ldb + j]
+  float* C; long long ldc;           // C[i*ldc + j]
+  const float* bias;                 // + bias[j]            (mode 0 only)
+  const float* add_src;              // + add_src[i*ldc + j] (mode 0 only; may alias C)
+  const float* mask;                 // product *= (mask[i*ldc + j] > 0)
+  long long I; int J; long long K;
+  int relu_a, relu_b;
+  int mode;                          // 0: C = v, 1: C += v, 2: atomicAdd(C, v) (split-K over gridDim.z)
+  long long k_per_split;
+};
+
+// C[I,J] (op)= sum_k A(i,k) * B(k,j)
+template <bool A_T, bool B_T>
+__global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long i0 = (long long)blockIdx.x * BM;
+  const int j0 = blockIdx.y * BN;
+  const long long kbeg = (long long)blockIdx.z * g.k_per_split;
+  const long long kend = kbeg + g.k_per_split < g.K ? kbeg + g.k_per_split : g.K;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (long long k0 = kbeg; k0 < kend; k0 += BK) {
+    float a[4], b[4];
+    if (A_T) {          // i contiguous: thread -> (k = tid / 32, 4 consecutive i)
+      const long long k = k0 + (tid >> 5);
+      const long long i = i0 + (tid & 31) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = (k < kend && i + e < g.I) ? g.A[k * g.lda + i + e] : 0.f;
+    } else {            // k contiguous: thread -> (i = tid / 2, 4 consecutive k)
+      const long long i = i0 + (tid >> 1);
+      const long long k = k0 + (tid & 1) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = (i < g.I && k + e < kend) ? g.A[i * g.lda + k + e] : 0.f;
+    }
+    if (!B_T) {         // j contiguous
+      const long long k = k0 + (tid >> 5);
+      const int j = j0 + (tid & 31) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) b[e] = (k < kend && j + e < g.J) ? g.B[k * g.ldb + j + e] : 0.f;
+    } else {            // k contiguous
+      const int j = j0 + (tid >> 1);
+      const long long k = k0 + (tid & 1) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) b[e] = (j < g.J && k + e < kend) ? g.B[(long long)j * g.ldb + k + e] : 0.f;
+    }
+    if (g.relu_a) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = fmaxf(a[e], 0.f);
+    }
+    if (g.relu_b) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) b[e] = fmaxf(b[e], 0.f);
+    }
+    if (A_T) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) As[tid >> 5][(tid & 31) * 4 + e] = a[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) As[(tid & 1) * 4 + e][tid >> 1] = a[e];
+    }
+    if (!B_T) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[tid >> 5][(tid & 31) * 4 + e] = b[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[(tid & 1) * 4 + e][tid >> 1] = b[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long gi = i0 + ty * 8 + i;
+    if (gi >= g.I) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gj = j0 + tx * 8 + j;
+      if (gj >= g.J) continue;
+      const long long o = gi * g.ldc + gj;
+      float v = acc[i][j];
+      if (g.mask && !(g.mask[o] > 0.f)) v = 0.f;
+      if (g.mode == 0) {
+        if (g.bias) v += g.bias[gj];
+        if (g.add_src) v += g.add_src[o];
+        g.C[o] = v;
+      } else if (g.mode == 1) {
+        g.C[o] += v;
+      } else {
+        atomicAdd(g.C + o, v);
+      }
+    }
+  }
+}
+
+static int launch_gemm(GemmArgs g, bool a_t, bool b_t, cudaStream_t st) {
+  if (g.I == 0 || g.J == 0) return PNR_OK;
+  int splits = 1;
+  g.k_per_split = g.K;
+  if (g.mode == 2) {                          // weight gradients: reduce over all rows, few output tiles -> split K
+    const long long tiles = ((g.I + BM - 1) / BM) * ((g.J + BN - 1) / BN);
+    long long want = (148 * 4 + tiles - 1) / tiles;
+    long long max_splits = (g.K + 1023) / 1024;
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    splits = (int)want;
+    g.k_per_split = ((g.K + splits - 1) / splits + BK - 1) / BK * BK;
+    splits = (int)((g.K + g.k_per_split - 1) / g.k_per_split);
+  }
+  dim3 grid((unsigned)((g.I + BM - 1) / BM), (unsigned)((g.J + BN - 1) / BN), (unsigned)splits);
+  if (a_t && b_t) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
+  else if (a_t) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
+  else if (b_t) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
+  else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(g);
+  PNR_CHECK_LAUNCH("bwd::sgemm_kernel");
+  return PNR_OK;
+}
+
+// Y[M,N] = relu?(X[M,K]) W[N,K]^T + bias (+ add_src)                       nn.Linear forward
+static int linear_fwd(const float* X, long long ldx, const float* W, const float* bias, const float* add_src, float* Y,
+                      long long M, int N, int K, bool relu_in, cudaStream_t st) {
+  GemmArgs g = {};
+  g.A = X; g.lda = ldx; g.B = W; g.ldb = K; g.C = Y; g.ldc = N; g.bias = bias; g.add_src = add_src;
+  g.I = M; g.J = N; g.K = K; g.relu_a = relu_in; g.mode = 0;
+  return launch_gemm(g, false, true, st);
+}
+// dX[M,K] (=|+=) (dY[M,N] W[N,K]) * (mask > 0)                              grad wrt the input of a Linear
+static int linear_bwd_input(const float* dY, const float* W, const float* mask, float* dX, long long M, int N, int K,
+                            bool accumulate, cudaStream_t st) {
+  GemmArgs g = {};
+  g.A = dY; g.lda = N; g.B = W; g.ldb = K; g.C = dX; g.ldc = K; g.mask = mask;
+  g.I = M; g.J = K; g.K = N; g.mode = accumulate ? 1 : 0;
+  return launch_gemm(g, false, false, st);
+}
+// dW[N,K] += dY[M,N]^T relu?(X[M,K])                                        grad wrt the weight of a Linear
+static int linear_bwd_weight(const float* dY, const float* X, long long ldx, float* dW, long long M, int N, int K,
+                             bool relu_x, cudaStream_t st) {
+  GemmArgs g = {};
+  g.A = dY; g.lda = N; g.B = X; g.ldb = ldx; g.C = dW; g.ldc = K;
+  g.I = N; g.J = K; g.K = M; g.relu_b = relu_x; g.mode = 2;
+  return launch_gemm(g, true, false, st);
+}
+
+// db[N] += column sums of dY[M,N]
+__global__ void colsum_kernel(const float* __restrict__ dY, float* __restrict__ db, long long M, int N, int rows_per_block) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += dY[r * N + j];
+    atomicAdd(db + j, acc);
+  }
+}
+static int colsum(const float* dY, float* db, long long M, int N, cudaStream_t st) {
+  if (M == 0) return PNR_OK;
+  const int rpb = 256;
+  colsum_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(dY, db, M, N, rpb);
+  PNR_CHECK_LAUNCH("bwd::colsum_kernel");
+  return PNR_OK;
+}
+
+// mean over the NS source views (util.py:489-499) and its transpose
+__global__ void view_mean_kernel(const float* __restrict__ x, float* __restrict__ y, int SB, int NS, int P, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)SB * P * H) return;
+  const int h = (int)(i % H);
+  const long long sp = i / H;
+  const int p = (int)(sp % P), s = (int)(sp / P);
+  float acc = 0.f;
+  for (int v = 0; v < NS; ++v) acc += x[(((long long)s * NS + v) * P + p) * H + h];
+  y[i] = acc / (float)NS;
+}
+__global__ void view_mean_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int SB, int NS, int P, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)SB * NS * P * H) return;
+  const int h = (int)(i % H);
+  const long long svp = i / H;
+  const int p = (int)(svp % P);
+  const int s = (int)(svp / P / NS);
+  dx[i] = dy[((long long)s * P + p) * H + h] / (float)NS;
+}
+
+// lin_out (H -> d_out <= 8) on relu(x), sigmoid(rgb) / relu(sigma)          resnetfc.py:185, models.py:312-317
+__global__ void lin_out_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                   float* __restrict__ out, long long rows, int H, int d_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  for (int o = 0; o < d_out; ++o) {
+    float acc = 0.f;
+    for (int k = lane; k < H; k += 32) acc = fmaf(fmaxf(x[row * H + k], 0.f), W[o * H + k], acc);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) {
+      float v = acc + bias[o];
+      out[row * d_out + o] = (o < 3) ? 1.0f / (1.0f + expf(-v)) : fmaxf(v, 0.f);
+    }
+  }
+}
+// One warp per point: d_raw = d_out * act'(out); dx = (d_raw W) * (x > 0); per-block partial dW / db -> atomics.
+__global__ void __launch_bounds__(256)
+lin_out_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ out,
+                   const float* __restrict__ d_out_act, float* __restrict__ dx, float* __restrict__ dW,
+                   float* __restrict__ db, long long rows, int H, int d_out, int rows_per_warp) {
+  extern __shared__ float sm[];                 // [d_out][H] partial dW of this block, then [d_out] partial db
+  float* sW = sm;
+  float* sb = sm + d_out * H;
+  for (int i = threadIdx.x; i < d_out * H + d_out; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const long long row = warp * rows_per_warp + rr;
+    if (row >= rows) break;
+    float draw[8];
+    for (int o = 0; o < d_out; ++o) {
+      const float y = out[row * d_out + o], gy = d_out_act[row * d_out + o];
+      draw[o] = (o < 3) ? gy * y * (1.0f - y) : (y > 0.f ? gy : 0.f);     // sigmoid' = y (1 - y); relu' = [y > 0]
+    }
+    if (lane == 0) for (int o = 0; o < d_out; ++o) atomicAdd(sb + o, draw[o]);
+    for (int k = lane; k < H; k += 32) {
+      const float xv = x[row * H + k];
+      const float r = fmaxf(xv, 0.f);
+      float g = 0.f;
+      for (int o = 0; o < d_out; ++o) {
+        g = fmaf(draw[o], W[o * H + k], g);
+        atomicAdd(sW + o * H + k, draw[o] * r);
+      }
+      dx[row * H + k] = xv > 0.f ? g : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d_out * H; i += blockDim.x) atomicAdd(dW + i, sW[i]);
+  for (int i = threadIdx.x; i < d_out; i += blockDim.x) atomicAdd(db + i, sb[i]);
+}
+
+// Backward of projection + bilinear gather + positional encoding for one (object, view, point) row per warp.
+//   dlat (rows, C), dzf (rows, d_in)  ->  d_feat (fp32 channels-last maps, atomics; may be null),
+//   d_xyz (SB*P, 3) (mode 0) or d_z (SB*B*K) (mode 1: x = o + z d  =>  dz = dx . d), atomics; may be null.
+__global__ void __launch_bounds__(256)
+gather_encode_bwd_kernel(pnr_scene sc, pnr_points q, const float* __restrict__ dlat, const float* __restrict__ dzf,
+                         float* __restrict__ d_feat, float* __restrict__ d_xyz, float* __restrict__ d_z, int num_freqs,
+                         float freq_factor, long long n_rows) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int NS = sc.NS, P = q.P, C = sc.C;
+  const int d_in = 6 * num_freqs + 6;
+  const bool want_x = d_xyz || d_z;
+  for (long long row = warp; row < n_rows; row += n_warps) {
+    const int view = (int)(row / P);
+    const int p = (int)(row - (long long)view * P);
+    const int s = view / NS;
+    const long long pidx = (long long)s * P + p;
+    float px, py, pz, vx, vy, vz;
+    fetch_point(q, pidx, px, py, pz, vx, vy, vz);
+    const Projection pr = project_point(sc, view, px, py, pz, vx, vy, vz);
+    const Taps t = make_taps(pr.ix, pr.iy, sc.Hl, sc.Wl, C);
+    const size_t map_off = (size_t)view * sc.Hl * sc.Wl * C;
+    const float* fm = (const float*)sc.feat + map_off;
+    float gix = 0.f, giy = 0.f;
+    const float fx0 = floorf(pr.ix), fy0 = floorf(pr.iy);
+    const float ax = pr.ix - fx0, ay = pr.iy - fy0;          // (ix - x0), (iy - y0); (x1 - ix) = 1 - ax
+    for (int c0 = lane * 4; c0 < C; c0 += 128) {
+      const float4 g = *reinterpret_cast<const float4*>(dlat + row * C + c0);
+      float4 f[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t.off[k] >= 0) {
+          if (want_x) f[k] = __ldg(reinterpret_cast<const float4*>(fm + t.off[k] + c0));
+          if (d_feat) {
+            float* dst = d_feat + map_off + t.off[k] + c0;
+            atomicAdd(dst + 0, t.w[k] * g.x); atomicAdd(dst + 1, t.w[k] * g.y);
+            atomicAdd(dst + 2, t.w[k] * g.z); atomicAdd(dst + 3, t.w[k] * g.w);
+          }
+        }
+      }
+      if (want_x) {
+        // d/dix = (ne - nw)(y1 - iy) + (se - sw)(iy - y0);  d/diy = (sw - nw)(x1 - ix) + (se - ne)(ix - x0)
+        const float bx = 1.0f - ax, by = 1.0f - ay;
+#define PNR_ACC(comp)                                                                              \
+        gix += g.comp * ((f[1].comp - f[0].comp) * by + (f[3].comp - f[2].comp) * ay);             \
+        giy += g.comp * ((f[2].comp - f[0].comp) * bx + (f[3].comp - f[1].comp) * ax);
+        PNR_ACC(x) PNR_ACC(y) PNR_ACC(z) PNR_ACC(w)
+#undef PNR_ACC
+      }
+    }
+    if (!want_x) continue;
+    // positional encoding: element j of the z-feature row depends on coordinate d = (j - 3) % 3 of R x
+    float gx[3] = {0.f, 0.f, 0.f};
+    const int n_pe = 3 + 6 * num_freqs;
+    for (int j = lane; j < n_pe && j < d_in; j += 32) {
+      const float gj = dzf[row * d_in + j];
+      if (j < 3) { gx[j] += gj; continue; }
+      const int qq = j - 3, k = qq / 6, r = qq - k * 6, d = r % 3;
+      const float xv = d == 0 ? pr.xr : (d == 1 ? pr.yr : pr.zr);
+      const float f = freq_factor * (float)(1 << k);
+      const float ph = r >= 3 ? 1.57079637050628662109375f : 0.0f;
+      const float dv = gj * f * cosf(fmaf(xv, f, ph));           // d/dx sin(f x + ph)
+      gx[d] += dv;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      gix += __shfl_xor_sync(0xffffffffu, gix, d);
+      giy += __shfl_xor_sync(0xffffffffu, giy, d);
+      gx[0] += __shfl_xor_sync(0xffffffffu, gx[0], d);
+      gx[1] += __shfl_xor_sync(0xffffffffu, gx[1], d);
+      gx[2] += __shfl_xor_sync(0xffffffffu, gx[2], d);
+    }
+    if (lane == 0) {
+      const float* M = sc.poses + (size_t)view * 12;
+      const float xc = pr.xr + M[3], yc = pr.yr + M[7], zc = pr.zr + M[11];
+      const float fxv = sc.focal[view * 2 + 0], fyv = sc.focal[view * 2 + 1];
+      // ix = u * (lat_scale_x / image_w) * 0.5 * (Wl - 1),  u = -xc / zc * fx + cx
+      const float du = gix * (sc.lat_scale_x / sc.image_w) * 0.5f * (float)(sc.Wl - 1);
+      const float dv = giy * (sc.lat_scale_y / sc.image_h) * 0.5f * (float)(sc.Hl - 1);
+      const float inv_z = 1.0f / zc;
+      float gc[3];
+      gc[0] = -fxv * inv_z * du;
+      gc[1] = -fyv * inv_z * dv;
+      gc[2] = (xc * fxv * du + yc * fyv * dv) * inv_z * inv_z;
+      if (!isfinite(gc[0]) || !isfinite(gc[1]) || !isfinite(gc[2])) gc[0] = gc[1] = gc[2] = 0.f;   // point on the camera plane
+      const float r0 = gx[0] + gc[0], r1 = gx[1] + gc[1], r2 = gx[2] + gc[2];
+      // x_rot = R x  =>  dx = R^T d(x_rot)
+      const float wx = M[0] * r0 + M[4] * r1 + M[8] * r2;
+      const float wy = M[1] * r0 + M[5] * r1 + M[9] * r2;
+      const float wz = M[2] * r0 + M[6] * r1 + M[10] * r2;
+      if (d_xyz) { atomicAdd(d_xyz + pidx * 3 + 0, wx); atomicAdd(d_xyz + pidx * 3 + 1, wy); atomicAdd(d_xyz + pidx * 3 + 2, wz); }
+      if (d_z) atomicAdd(d_z + pidx, wx * vx + wy * vy + wz * vz);
+    }
+  }
+}
+
+struct Tape {
+  float *lat, *zf;
+  float* X[9];      // rows x H: input of pre-combine block b (b < CL); X[CL] = output of the last pre-combine block
+  float* NET[8];    // rows x H: fc_0 output of pre-combine block b
+  float* XM[9];     // pts x H : input of post-combine block b (b >= CL); XM[n_blocks] = input of lin_out
+  float* NETM[8];   // pts x H
+  size_t floats;
+};
+static Tape carve_tape(float* base, long long rows, long long pts, int C, int d_in, int H, int nb, int CL) {
+  Tape t = {};
+  float* p = base;
+  t.lat = p; p += rows * C;
+  t.zf = p; p += rows * d_in;
+  for (int b = 0; b <= CL; ++b) { t.X[b] = p; p += rows * H; }
+  for (int b = 0; b < CL; ++b) { t.NET[b] = p; p += rows * H; }
+  for (int b = CL; b <= nb; ++b) { t.XM[b] = p; p += pts * H; }
+  for (int b = CL; b < nb; ++b) { t.NETM[b] = p; p += pts * H; }
+  t.floats = (size_t)(p - base);
+  return t;
+}
+
+static int check_train(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, int num_freqs, const char* who) {
+  int rc = validate_scene_points(sc, q, who);
+  if (rc) return rc;
+  PNR_REQUIRE(mp, PNR_ERR_ARG, "%s: null params", who);
+  PNR_REQUIRE(sc->feat_fp32, PNR_ERR_ARG, "%s: the training path reads fp32 channels-last feature maps", who);
+  PNR_REQUIRE(sc->C % 4 == 0, PNR_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 4", who, sc->C);
+  PNR_REQUIRE(mp->d_latent == sc->C, PNR_ERR_ARG, "%s: d_latent=%d but maps have C=%d", who, mp->d_latent, sc->C);
+  PNR_REQUIRE(mp->d_in == 6 * num_freqs + 6, PNR_ERR_ARG, "%s: d_in/num_freqs mismatch", who);
+  PNR_REQUIRE(mp->n_blocks >= 1 && mp->n_blocks <= 8, PNR_ERR_UNSUPPORTED, "%s: n_blocks=%d", who, mp->n_blocks);
+  PNR_REQUIRE(mp->combine_layer >= 1 && mp->combine_layer <= mp->n_blocks, PNR_ERR_ARG, "%s: combine_layer=%d", who, mp->combine_layer);
+  PNR_REQUIRE(mp->combine_layer < mp->n_blocks || sc->NS == 1, PNR_ERR_UNSUPPORTED, "%s: combine_layer >= n_blocks needs NS=1", who);
+  PNR_REQUIRE(mp->d_out >= 1 && mp->d_out <= 8, PNR_ERR_UNSUPPORTED, "%s: d_out=%d", who, mp->d_out);
+  PNR_REQUIRE((long long)sc->SB * sc->NS * q->P < (1LL << 31), PNR_ERR_ARG, "%s: too many rows per call", who);
+  return PNR_OK;
+}
+
+}  // namespace bwd
+}  // namespace pnr
+
+using namespace pnr;
+using namespace pnr::bwd;
+
+extern "C" size_t pnr_field_tape_bytes(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp) {
+  if (!sc || !q || !mp) return 0;
+  const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
+  return carve_tape(nullptr, rows, pts, sc->C, mp->d_in, mp->d_hidden, mp->n_blocks, mp->combine_layer).floats * sizeof(float) + 256;
+}
+
+extern "C" int pnr_field_forward_train(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, float* out,
+                                       void* tape, size_t tape_bytes, int num_freqs, float freq_factor, void* stream) {
+  reset_launch_count();
+  int rc = check_train(sc, q, mp, num_freqs, "pnr_field_forward_train");
+  if (rc) return rc;
+  PNR_REQUIRE(out && tape && tape_bytes >= pnr_field_tape_bytes(sc, q, mp), PNR_ERR_ARG, "pnr_field_forward_train: tape too small");
+  const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
+  if (pts == 0) return PNR_OK;
+  const int H = mp->d_hidden, C = sc->C, d_in = mp->d_in, nb = mp->n_blocks, CL = mp->combine_layer;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Tape t = carve_tape((float*)tape, rows, pts, C, d_in, H, nb, CL);
+  int launches = 0;
+  rc = pnr_gather_encode(sc, q, t.lat, t.zf, 1, num_freqs, freq_factor, stream);
+  if (rc) return rc;
+  launches += 1;
+#define STEP(call) do { rc = (call); if (rc) return rc; ++launches; } while (0)
+  STEP(linear_fwd(t.zf, d_in, mp->lin_in_w, mp->lin_in_b, nullptr, t.X[0], rows, H, d_in, false, st));        // resnetfc.py:149
+  for (int b = 0; b < CL; ++b) {
+    STEP(linear_fwd(t.lat, C, mp->linz_w[b], mp->linz_b[b], t.X[b], t.X[b], rows, H, C, false, st));          // x += lin_z[b](z)
+    STEP(linear_fwd(t.X[b], H, mp->fc0_w[b], mp->fc0_b[b], nullptr, t.NET[b], rows, H, H, true, st));          // resnetfc.py:55
+    STEP(linear_fwd(t.NET[b], H, mp->fc1_w[b], mp->fc1_b[b], t.X[b], t.X[b + 1], rows, H, H, true, st));       // resnetfc.py:56,62
+  }
+  {
+    const long long n = pts * H;
+    view_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.X[CL], t.XM[CL], sc->SB, sc->NS, q->P, H);  // util.py:489-499
+    PNR_CHECK_LAUNCH("bwd::view_mean_kernel");
+    ++launches;
+  }
+  for (int b = CL; b < nb; ++b) {
+    STEP(linear_fwd(t.XM[b], H, mp->fc0_w[b], mp->fc0_b[b], nullptr, t.NETM[b], pts, H, H, true, st));
+    STEP(linear_fwd(t.NETM[b], H, mp->fc1_w[b], mp->fc1_b[b], t.XM[b], t.XM[b + 1], pts, H, H, true, st));
+  }
+  lin_out_fwd_kernel<<<(unsigned)((pts * 32 + 255) / 256), 256, 0, st>>>(t.XM[nb], mp->lin_out_w, mp->lin_out_b, out, pts, H, mp->d_out);
+  PNR_CHECK_LAUNCH("bwd::lin_out_fwd_kernel");
+  ++launches;
+  reset_launch_count();
+  count_launch(launches);
+  return PNR_OK;
+}
+
+extern "C" size_t pnr_field_backward_workspace_bytes(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp) {
+  if (!sc || !q || !mp) return 0;
+  const size_t rows = (size_t)sc->SB * sc->NS * q->P;
+  return sizeof(float) * rows * (2 * (size_t)mp->d_hidden + (size_t)sc->C + (size_t)mp->d_in) + 256;
+}
+
+extern "C" int pnr_field_backward(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const void* tape,
+                                  const float* out, const float* d_out, const pnr_mlp_grads* gr, float* d_feat,
+                                  float* d_xyz, float* d_z, void* workspace, size_t workspace_bytes, int num_freqs,
+                                  float freq_factor, void* stream) {
+  reset_launch_count();
+  int rc = check_train(sc, q, mp, num_freqs, "pnr_field_backward");
+  if (rc) return rc;
+  PNR_REQUIRE(tape && out && d_out && gr, PNR_ERR_ARG, "pnr_field_backward: null pointer");
+  PNR_REQUIRE(workspace && workspace_bytes >= pnr_field_backward_workspace_bytes(sc, q, mp), PNR_ERR_ARG,
+              "pnr_field_backward: workspace too small");
+  PNR_REQUIRE(!(d_xyz && q->mode != 0) && !(d_z && q->mode != 1), PNR_ERR_ARG,
+              "pnr_field_backward: d_xyz goes with explicit points (mode 0), d_z with rays x depths (mode 1)");
+  const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
+  if (pts == 0) return PNR_OK;
+  const int H = mp->d_hidden, C = sc->C, d_in = mp->d_in, nb = mp->n_blocks, CL = mp->combine_layer, NS = sc->NS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Tape t = carve_tape((float*)const_cast<void*>(tape), rows, pts, C, d_in, H, nb, CL);
+  float* dA = (float*)workspace;            // current dx
+  float* dB = dA + rows * H;                // dnet / scratch
+  float* dlat = dB + rows * H;
+  float* dzf = dlat + rows * C;
+  int launches = 0;
+  {
+    const int rpw = 4;
+    const long long warps = (pts + rpw - 1) / rpw;
+    const size_t smem = (size_t)(mp->d_out * H + mp->d_out) * sizeof(float);
+    lin_out_bwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, smem, st>>>(t.XM[nb], mp->lin_out_w, out, d_out, dA,
+                                                                                gr->lin_out_w, gr->lin_out_b, pts, H, mp->d_out, rpw);
+    PNR_CHECK_LAUNCH("bwd::lin_out_bwd_kernel");
+    ++launches;
+  }
+  // one residual block backwards (resnetfc.py:53-62): dx is updated in place, dn is scratch
+  auto block_bwd = [&](const float* Xb, const float* NETb, int b, float* dx, float* dn, long long M) -> int {
+    int r;
+    if ((r = linear_bwd_weight(dx, NETb, H, gr->fc1_w[b], M, H, H, true, st))) return r;
+    if ((r = colsum(dx, gr->fc1_b[b], M, H, st))) return r;
+    if ((r = linear_bwd_input(dx, mp->fc1_w[b], NETb, dn, M, H, H, false, st))) return r;
+    if ((r = linear_bwd_weight(dn, Xb, H, gr->fc0_w[b], M, H, H, true, st))) return r;
+    if ((r = colsum(dn, gr->fc0_b[b], M, H, st))) return r;
+    if ((r = linear_bwd_input(dn, mp->fc0_w[b], Xb, dx, M, H, H, true, st))) return r;
+    launches += 6;
+    return PNR_OK;
+  };
+  for (int b = nb - 1; b >= CL; --b)
+    if ((rc = block_bwd(t.XM[b], t.NETM[b], b, dA, dB, pts))) return rc;
+  {
+    const long long n = rows * H;
+    view_mean_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dA, dB, sc->SB, NS, q->P, H);
+    PNR_CHECK_LAUNCH("bwd::view_mean_bwd_kernel");
+    ++launches;
+    float* tmp = dA; dA = dB; dB = tmp;
+  }
+  for (int b = CL - 1; b >= 0; --b) {
+    if ((rc = block_bwd(t.X[b], t.NET[b], b, dA, dB, rows))) return rc;
+    STEP(linear_bwd_weight(dA, t.lat, C, gr->linz_w[b], rows, H, C, false, st));      // x += lin_z[b](z): resnetfc.py:176-182
+    STEP(colsum(dA, gr->linz_b[b], rows, H, st));
+    STEP(linear_bwd_input(dA, mp->linz_w[b], nullptr, dlat, rows, H, C, b != CL - 1, st));
+  }
+  STEP(linear_bwd_weight(dA, t.zf, d_in, gr->lin_in_w, rows, H, d_in, false, st));
+  STEP(colsum(dA, gr->lin_in_b, rows, H, st));
+  STEP(linear_bwd_input(dA, mp->lin_in_w, nullptr, dzf, rows, H, d_in, false, st));
+#undef STEP
+  if (d_feat || d_xyz || d_z) {
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    gather_encode_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(*sc, *q, dlat, dzf, d_feat, d_xyz, d_z, num_freqs, freq_factor, rows);
+    PNR_CHECK_LAUNCH("bwd::gather_encode_bwd_kernel");
+    ++launches;
+  }
+  reset_launch_count();
+  count_launch(launches);
+  return PNR_OK;
+}

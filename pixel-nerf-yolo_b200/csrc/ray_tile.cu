@@ -190,6 +190,122 @@ sample_fine_kernel(const float* __restrict__ weights, const float* __restrict__ 
   for (int i = lane; i < Ktot; i += 32) z_out[(size_t)b * Ktot + i] = srt[i];
 }
 
+
+// Backward of composite (nerf.py:184-188, 229-255), one warp per ray.  Given d rgb (B,3), d depth (B) and optionally
+// d weights (B,K):   dw_i = d_rgb . c_i + d_depth z_i + d_weights_i - [white] sum(d_rgb)
+//                    dalpha_i = dw_i T_i - (sum_{j>i} dw_j w_j) / (1 - alpha_i + 1e-10)        (w_j = alpha_j T_j)
+//                    dsigma_i = dalpha_i delta_i (1 - alpha_i) [sigma_i > 0],   ddelta_i = dalpha_i relu(sigma_i) (1 - alpha_i)
+//                    dz_i = w_i d_depth + ddelta_{i-1} - ddelta_i          (delta_i = z_{i+1} - z_i, last: far - z_K)
+// alpha and T are recomputed exactly as composite_kernel does; the suffix sum runs in double.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_kernel(const float4* __restrict__ rgb_sigma, const float* __restrict__ z, const float* __restrict__ rays,
+                     const float* __restrict__ d_rgb, const float* __restrict__ d_depth, const float* __restrict__ d_weights,
+                     float4* __restrict__ d_rgb_sigma, float* __restrict__ d_z, int B, int K, int white_bkgd) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * kWarpsPerBlock + wid;
+  if (b >= B) return;
+  float* sT = smem + (size_t)wid * 3 * K;      // T_i
+  float* sA = sT + K;                          // alpha_i
+  float* sD = sA + K;                          // ddelta_i
+  const float far = rays[b * 8 + 7];
+  const float* zr = z + (size_t)b * K;
+  const float4* o = rgb_sigma + (size_t)b * K;
+  const float gr = d_rgb[b * 3 + 0], gg = d_rgb[b * 3 + 1], gb = d_rgb[b * 3 + 2];
+  const float gd = d_depth ? d_depth[b] : 0.f;
+  const float gwhite = white_bkgd ? (gr + gg + gb) : 0.f;
+  double carry = 1.0;
+  for (int base = 0; base < K; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < K;
+    float alpha = 0.f;
+    if (valid) {
+      const float zi = zr[i];
+      const float znext = (i + 1 < K) ? zr[i + 1] : far;
+      const float delta = __fsub_rn(znext, zi);
+      const float sig = fmaxf(o[i].w, 0.0f);
+      alpha = __fsub_rn(1.0f, expf(__fmul_rn(-delta, sig)));
+    }
+    const float a_shift = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+    const double incl = warp_incl_scan_mul<double>((double)a_shift, lane);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0;
+    if (valid) { sT[i] = (float)(carry * excl); sA[i] = alpha; }
+    carry = carry * __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  double suffix = 0.0;                          // sum_{j > current chunk} dw_j w_j
+  const int n_chunks = (K + 31) / 32;
+  for (int ch = n_chunks - 1; ch >= 0; --ch) {
+    const int i = ch * 32 + lane;
+    const bool valid = i < K;
+    float dw = 0.f, w = 0.f, T = 0.f, alpha = 0.f, zi = 0.f, delta = 0.f;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      c = o[i]; zi = zr[i]; T = sT[i]; alpha = sA[i];
+      const float znext = (i + 1 < K) ? zr[i + 1] : far;
+      delta = __fsub_rn(znext, zi);
+      w = alpha * T;
+      dw = gr * c.x + gg * c.y + gb * c.z + gd * zi - gwhite + (d_weights ? d_weights[(size_t)b * K + i] : 0.f);
+    }
+    // inclusive suffix scan of dw*w within the chunk (lanes above), then make it exclusive
+    double v = (double)dw * (double)w;
+    double incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_down_sync(0xffffffffu, incl, d);
+      if (lane + d < 32) incl += t;
+    }
+    const double S = suffix + (incl - v);
+    suffix += __shfl_sync(0xffffffffu, incl, 0);
+    if (valid) {
+      const float one_m = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      const float dalpha = dw * T - (float)(S / (double)one_m);
+      const float keep = 1.0f - alpha;          // d alpha / d (delta * sigma) = exp(-delta sigma) = 1 - alpha
+      const float sig = fmaxf(c.w, 0.0f);
+      const float dsig = (c.w > 0.0f) ? dalpha * delta * keep : 0.0f;
+      sD[i] = dalpha * sig * keep;
+      d_rgb_sigma[(size_t)b * K + i] = make_float4(w * gr, w * gg, w * gb, dsig);
+    }
+  }
+  if (d_z) {
+    __syncwarp();
+    for (int i = lane; i < K; i += 32) {
+      const float w = sA[i] * sT[i];
+      d_z[(size_t)b * K + i] = w * gd + (i > 0 ? sD[i - 1] : 0.f) - sD[i];
+    }
+  }
+}
+
+// Backward of sample_fine_depth + cat + sort (nerf.py:156-167, 296-301) with respect to the coarse depth: the Kfd depth
+// samples are z_j = clamp(depth + gauss_j * depth_std, near, far); sample j sits at the position of its value in the
+// sorted row, and passes the gradient on unless it was clamped.  (sample_fine is fed detached weights, nerf.py:136,293.)
+__global__ void sample_depth_bwd_kernel(const float* __restrict__ z_sorted, const float* __restrict__ d_z_sorted,
+                                        const float* __restrict__ depth, const float* __restrict__ gauss,
+                                        const float* __restrict__ rays, float* __restrict__ d_depth, int B, int K, int Kfd,
+                                        float depth_std) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float near = rays[b * 8 + 6], far = rays[b * 8 + 7], d = depth[b];
+  const float* zs = z_sorted + (size_t)b * K;
+  float acc = 0.f;
+  for (int j = lane; j < Kfd; j += 32) {
+    const float raw = __fadd_rn(d, __fmul_rn(gauss[(size_t)b * Kfd + j], depth_std));
+    if (!(raw > near && raw < far)) continue;                 // clamped (or NaN): no gradient
+    int lo = 0, hi = K;                                       // first position with zs[pos] >= raw
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (zs[mid] < raw) lo = mid + 1; else hi = mid; }
+    int rank = 0;                                             // equal depth samples occupy consecutive positions
+    for (int jj = 0; jj < j; ++jj)
+      if (__fadd_rn(d, __fmul_rn(gauss[(size_t)b * Kfd + jj], depth_std)) == raw) ++rank;
+    const int pos = lo + rank;
+    if (pos < K && zs[pos] == raw) acc += d_z_sorted[(size_t)b * K + pos];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) d_depth[b] = acc;
+}
+
 }  // namespace pnr
 
 using namespace pnr;
@@ -240,5 +356,33 @@ extern "C" int pnr_sample_fine(const float* weights, const float* depth, const f
                        (cudaStream_t)stream>>>(weights, depth, rays, z_coarse, u, jitter, gauss, z_out, inds_out,
                                                z_fine_out, z_depth_out, B, Kc, Kf, Kfd, depth_std, lindisp, n_pad);
   PNR_CHECK_LAUNCH("sample_fine_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_composite_backward(const float* rgb_sigma, const float* z, const float* rays, const float* d_rgb,
+                                      const float* d_depth, const float* d_weights, float* d_rgb_sigma, float* d_z,
+                                      int B, int K, int white_bkgd, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(rgb_sigma && z && rays && d_rgb && d_rgb_sigma, PNR_ERR_ARG, "pnr_composite_backward: null pointer");
+  PNR_REQUIRE(B >= 0 && K > 0 && K <= 1024, PNR_ERR_ARG, "pnr_composite_backward: bad shape B=%d K=%d", B, K);
+  if (B == 0) return PNR_OK;
+  const size_t smem = (size_t)kWarpsPerBlock * 3 * K * sizeof(float);
+  composite_bwd_kernel<<<(B + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      (const float4*)rgb_sigma, z, rays, d_rgb, d_depth, d_weights, (float4*)d_rgb_sigma, d_z, B, K, white_bkgd);
+  PNR_CHECK_LAUNCH("composite_bwd_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_sample_fine_depth_backward(const float* z_sorted, const float* d_z_sorted, const float* depth,
+                                              const float* gauss, const float* rays, float* d_depth, int B, int K,
+                                              int Kfd, float depth_std, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(z_sorted && d_z_sorted && depth && gauss && rays && d_depth, PNR_ERR_ARG,
+              "pnr_sample_fine_depth_backward: null pointer");
+  PNR_REQUIRE(B >= 0 && K > 0 && Kfd > 0 && Kfd <= K, PNR_ERR_ARG, "pnr_sample_fine_depth_backward: bad shape");
+  if (B == 0) return PNR_OK;
+  sample_depth_bwd_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(z_sorted, d_z_sorted, depth, gauss, rays,
+                                                                         d_depth, B, K, Kfd, depth_std);
+  PNR_CHECK_LAUNCH("sample_depth_bwd_kernel");
   return PNR_OK;
 }

@@ -16,6 +16,67 @@ from .code import PositionalEncoding
 from .model_util import make_encoder, make_mlp
 
 
+class _FieldTrainFn(torch.autograd.Function):
+    """PixelNeRFNet.forward with a backward pass (BASELINE config 3): ``pnr_field_forward_train`` keeps the
+    activations on a tape, ``pnr_field_backward`` produces what autograd produces for the reference --
+    gradients of the ResnetFC parameters, of the feature maps and of the sample depths / query points."""
+
+    @staticmethod
+    def forward(ctx, net, mlp, mode, sb, feat, a, b, *params):
+        lib = _lib.load()
+        dev = feat.device
+        sc, keep = net._scene_for(feat, fp32_maps=True)
+        pts = _lib.Points()
+        if mode == "rays":          # a = rays (SB*B, 8), b = z (SB*B, K)
+            K = b.shape[1]
+            P = (a.shape[0] // sb) * K
+            pts.rays, pts.z, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 1, P, K
+        else:                       # a = xyz (SB, P, 3), b = viewdirs (SB, P, 3)
+            P = a.shape[1]
+            pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 0, P, 0
+        cp = mlp.c_params()
+        out = torch.empty(sb, P, 4, device=dev, dtype=torch.float32)
+        tape = torch.empty(lib.pnr_field_tape_bytes(sc, pts, cp), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.pnr_field_forward_train(sc, pts, cp, out.data_ptr(), tape.data_ptr(), tape.numel(),
+                                             net.code.num_freqs, net.code.freq_factor, _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_field_forward_train")
+        net.last_launches = lib.pnr_last_launch_count()
+        ctx.net, ctx.mlp, ctx.mode, ctx.sb, ctx.P = net, mlp, mode, sb, P
+        ctx.keep = keep
+        ctx.save_for_backward(feat, a, b, out, tape, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        feat, a, b, out, tape, *params = ctx.saved_tensors
+        net, mlp, mode, sb, P = ctx.net, ctx.mlp, ctx.mode, ctx.sb, ctx.P
+        dev = feat.device
+        sc, _keep = net._scene_for(feat, fp32_maps=True, cams=ctx.keep)
+        pts = _lib.Points()
+        if mode == "rays":
+            pts.rays, pts.z, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 1, P, b.shape[1]
+        else:
+            pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 0, P, 0
+        cp = mlp.c_params()
+        grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
+        need_feat, need_a, need_b = ctx.needs_input_grad[4], ctx.needs_input_grad[5], ctx.needs_input_grad[6]
+        d_feat = torch.zeros_like(feat) if need_feat else None
+        d_xyz = torch.zeros_like(a) if (mode == "xyz" and need_a) else None
+        d_z = torch.zeros_like(b) if (mode == "rays" and need_b) else None
+        ws = torch.empty(lib.pnr_field_backward_workspace_bytes(sc, pts, cp), dtype=torch.uint8, device=dev)
+        d_out = d_out.contiguous().float()
+        with torch.cuda.device(dev):
+            rc = lib.pnr_field_backward(sc, pts, cp, tape.data_ptr(), out.data_ptr(), d_out.data_ptr(),
+                                        mlp.c_grads(grads), _lib.ptr(d_feat), _lib.ptr(d_xyz), _lib.ptr(d_z),
+                                        ws.data_ptr(), ws.numel(), net.code.num_freqs, net.code.freq_factor,
+                                        _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_field_backward")
+        net.last_bwd_launches = getattr(net, "last_bwd_launches", 0) + lib.pnr_last_launch_count()
+        return (None, None, None, None, d_feat, d_xyz, d_z, *grads)
+
+
 class PixelNeRFNet(torch.nn.Module):
     def __init__(self, conf, stop_encoder_grad=False):
         super().__init__()
@@ -112,6 +173,11 @@ class PixelNeRFNet(torch.nn.Module):
     # ------------------------------------------------------------------------------------------------
     def _scene(self, fp32_maps: bool):
         """pnr_scene view of the encoded state (+ the tensors that must stay alive during the call)."""
+        return self._scene_for(self.encoder.packed_latent(fp32=fp32_maps), fp32_maps)
+
+    def _scene_for(self, feat, fp32_maps: bool, cams=None):
+        """pnr_scene over an explicit channels-last feature tensor (the training path passes the autograd-tracked
+        fp32 copy); ``cams`` re-uses the camera tensors captured at forward time."""
         n_views = self.poses.shape[0]
         NS = self.num_views_per_obj
         SB = n_views // NS
@@ -129,15 +195,14 @@ class PixelNeRFNet(torch.nn.Module):
             self._cam_cache = (self.poses.contiguous(), per_view(self.focal), per_view(self.c),
                                float(self.image_shape[0]), float(self.image_shape[1]),
                                float(self.encoder.latent_scaling[0]), float(self.encoder.latent_scaling[1]))
-        poses, focal, center, iw, ih, lsx, lsy = self._cam_cache
-        feat = self.encoder.packed_latent(fp32=fp32_maps)
+        poses, focal, center, iw, ih, lsx, lsy = cams if cams is not None else self._cam_cache
         assert feat.shape[0] == n_views, "encoder.latent and poses disagree on the number of views"
         sc = _lib.Scene()
         sc.feat, sc.poses, sc.focal, sc.center = feat.data_ptr(), poses.data_ptr(), focal.data_ptr(), center.data_ptr()
         sc.SB, sc.NS, sc.C, sc.Hl, sc.Wl = SB, NS, feat.shape[3], feat.shape[1], feat.shape[2]
         sc.feat_fp32 = int(fp32_maps)
         sc.image_w, sc.image_h, sc.lat_scale_x, sc.lat_scale_y = iw, ih, lsx, lsy
-        return sc, (feat, poses, focal, center)
+        return sc, (poses, focal, center, iw, ih, lsx, lsy)
 
     def _mlp(self, coarse):
         return self.mlp_coarse if (coarse or self.mlp_fine is None) else self.mlp_fine
@@ -181,10 +246,11 @@ class PixelNeRFNet(torch.nn.Module):
         SB, B, _ = xyz.shape
         assert viewdirs is not None
         _lib.require_cuda(xyz, "xyz")
-        if torch.is_grad_enabled() and (xyz.requires_grad or any(p.requires_grad for p in self._mlp(coarse).parameters())):
-            if self.training:
-                raise NotImplementedError("PixelNeRFNet (B200 path): backward is not built yet; wrap inference in "
-                                          "torch.no_grad() (the training step is SURVEY.md section 7 step 7)")
+        if self._wants_grad(coarse, xyz):
+            assert SB * self.num_views_per_obj == self.poses.shape[0], "call encode() first"
+            mlp = self._mlp(coarse)
+            return _FieldTrainFn.apply(self, mlp, "xyz", SB, self._train_feat(), xyz.contiguous().float(),
+                                       viewdirs.detach().reshape(SB, B, 3).contiguous().float(), *mlp.ordered_params())
         xyz = xyz.detach().contiguous().float()
         viewdirs = viewdirs.detach().reshape(SB, B, 3).contiguous().float()
         assert SB * self.num_views_per_obj == self.poses.shape[0], "call encode() first"
@@ -197,6 +263,24 @@ class PixelNeRFNet(torch.nn.Module):
             outs.append(self._run_field(pts, SB, xs.shape[1], coarse, (xs, ds)))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
+    def _wants_grad(self, coarse, *tensors):
+        """True when this call must record a backward pass (the reference just runs under autograd)."""
+        if not (torch.is_grad_enabled() and self.training):      # inference callers use .eval() and/or no_grad()
+            return False
+        if any(t is not None and t.requires_grad for t in tensors):
+            return True
+        if any(p.requires_grad for p in self._mlp(coarse).parameters()):
+            return True
+        return self.encoder.latent.requires_grad and not self.stop_encoder_grad
+
+    def _train_feat(self):
+        """fp32 channels-last view of encoder.latent that autograd can differentiate through (a permute + copy in
+        torch: plumbing; models.py:242-243 detaches it when stop_encoder_grad is set)."""
+        lat = self.encoder.latent
+        if self.stop_encoder_grad:
+            lat = lat.detach()
+        return lat.float().permute(0, 2, 3, 1).contiguous()
+
     def field_from_rays(self, rays, z, coarse=True, sb=1):
         """Renderer fast path: evaluate the field at o + z*d for rays (SB*B, 8), z (SB*B, K) without ever
         materialising the points (nerf.py:191-222 folded into the kernel's point fetch).  -> (SB*B, K, 4)."""
@@ -205,6 +289,10 @@ class PixelNeRFNet(torch.nn.Module):
         Bp = Bt // sb
         rays = rays.contiguous().float()
         z = z.contiguous().float()
+        if self._wants_grad(coarse, z):
+            mlp = self._mlp(coarse)
+            return _FieldTrainFn.apply(self, mlp, "rays", sb, self._train_feat(), rays.detach(), z,
+                                       *mlp.ordered_params()).reshape(Bt, K, 4)
         if self.precision == "bf16":
             pts = _lib.Points()
             pts.rays, pts.z, pts.mode, pts.P, pts.K = rays.data_ptr(), z.data_ptr(), 1, Bp * K, K

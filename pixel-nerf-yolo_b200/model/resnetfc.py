@@ -75,6 +75,26 @@ class ResnetFC(nn.Module):
         p.n_blocks, p.combine_layer = self.n_blocks, min(self.combine_layer, self.n_blocks)
         return p
 
+    def ordered_params(self):
+        """Parameters in the fixed order the training-path autograd function passes them (and returns grads)."""
+        ps = [self.lin_in.weight, self.lin_in.bias, self.lin_out.weight, self.lin_out.bias]
+        for blk in self.blocks:
+            ps += [blk.fc_0.weight, blk.fc_0.bias, blk.fc_1.weight, blk.fc_1.bias]
+        for lz in self.lin_z:
+            ps += [lz.weight, lz.bias]
+        return ps
+
+    def c_grads(self, grads):
+        """pnr_mlp_grads over a list of fp32 accumulators in ``ordered_params`` order."""
+        g = _lib.MlpGrads()
+        it = iter(t.data_ptr() for t in grads)
+        g.lin_in_w, g.lin_in_b, g.lin_out_w, g.lin_out_b = next(it), next(it), next(it), next(it)
+        for i in range(len(self.blocks)):
+            g.fc0_w[i], g.fc0_b[i], g.fc1_w[i], g.fc1_b[i] = next(it), next(it), next(it), next(it)
+        for i in range(len(self.lin_z)):
+            g.linz_w[i], g.linz_b[i] = next(it), next(it)
+        return g
+
     def _param_key(self):
         return tuple((q.data_ptr(), q._version) for q in self.parameters())
 

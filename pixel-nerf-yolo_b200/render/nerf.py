@@ -13,6 +13,84 @@ from .. import _lib
 from ..conf import DotMap
 
 
+class _CompositeFn(torch.autograd.Function):
+    """composite (nerf.py:184-188, 229-255) with the backward pass autograd derives for the reference."""
+
+    @staticmethod
+    def forward(ctx, out, z, rays, white_bkgd):
+        lib = _lib.load()
+        B, K = z.shape
+        dev = z.device
+        out, z = out.contiguous(), z.contiguous()
+        w = torch.empty(B, K, device=dev, dtype=torch.float32)
+        rgb = torch.empty(B, 3, device=dev, dtype=torch.float32)
+        depth = torch.empty(B, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            rc = lib.pnr_composite(out.data_ptr(), z.data_ptr(), rays.data_ptr(), w.data_ptr(), rgb.data_ptr(),
+                                   depth.data_ptr(), B, K, int(bool(white_bkgd)), _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_composite")
+        ctx.white = int(bool(white_bkgd))
+        ctx.save_for_backward(out, z, rays)
+        return w, rgb, depth
+
+    @staticmethod
+    def backward(ctx, d_w, d_rgb, d_depth):
+        lib = _lib.load()
+        out, z, rays = ctx.saved_tensors
+        B, K = z.shape
+        dev = z.device
+        c = lambda t: None if t is None else t.contiguous().float()
+        d_w, d_rgb, d_depth = c(d_w), c(d_rgb), c(d_depth)
+        if d_rgb is None:
+            d_rgb = torch.zeros(B, 3, device=dev)
+        d_out = torch.empty_like(out)
+        d_z = torch.empty_like(z) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(dev):
+            rc = lib.pnr_composite_backward(out.data_ptr(), z.data_ptr(), rays.data_ptr(), d_rgb.data_ptr(),
+                                            _lib.ptr(d_depth), _lib.ptr(d_w), d_out.data_ptr(), _lib.ptr(d_z), B, K,
+                                            ctx.white, _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_composite_backward")
+        return d_out, d_z, None, None
+
+
+class _ResampleFn(torch.autograd.Function):
+    """sample_fine + sample_fine_depth + cat + sort (nerf.py:126-167, 290-301).  Only the coarse depth carries a
+    gradient: the importance sampler is fed detached weights (nerf.py:136, 293)."""
+
+    @staticmethod
+    def forward(ctx, depth, weights, rays, z_coarse, u, jitter, gauss, kf, kfd, depth_std, lindisp):
+        lib = _lib.load()
+        B, Kc = z_coarse.shape
+        dev = rays.device
+        z_out = torch.empty(B, Kc + kf + kfd, device=dev, dtype=torch.float32)
+        c = lambda t: None if t is None else t.contiguous().data_ptr()
+        depth = depth.contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.pnr_sample_fine(c(weights), depth.data_ptr(), rays.data_ptr(), z_coarse.data_ptr(), c(u), c(jitter),
+                                     c(gauss), z_out.data_ptr(), None, None, None, B, Kc, kf, kfd, float(depth_std),
+                                     int(lindisp), _lib.stream_ptr(dev))
+        _lib.check(rc, "pnr_sample_fine")
+        ctx.kfd, ctx.depth_std = kfd, float(depth_std)
+        ctx.save_for_backward(z_out, depth, gauss.contiguous() if gauss is not None else None, rays)
+        return z_out
+
+    @staticmethod
+    def backward(ctx, d_z):
+        z_out, depth, gauss, rays = ctx.saved_tensors
+        d_depth = None
+        if ctx.kfd > 0 and ctx.needs_input_grad[0]:
+            lib = _lib.load()
+            B, K = z_out.shape
+            d_depth = torch.empty_like(depth)
+            d_z = d_z.contiguous().float()
+            with torch.cuda.device(rays.device):
+                rc = lib.pnr_sample_fine_depth_backward(z_out.data_ptr(), d_z.data_ptr(), depth.data_ptr(), gauss.data_ptr(),
+                                                        rays.data_ptr(), d_depth.data_ptr(), B, K, ctx.kfd, ctx.depth_std,
+                                                        _lib.stream_ptr(rays.device))
+            _lib.check(rc, "pnr_sample_fine_depth_backward")
+        return (d_depth,) + (None,) * 10
+
+
 class _RenderWrapper(torch.nn.Module):
     """nerf.py:21-48: binds a network to a renderer; call signature ``(rays, want_weights=False)``."""
 
@@ -142,6 +220,8 @@ class NeRFRenderer(torch.nn.Module):
         sb = rays.shape[0]
         rays = rays.reshape(-1, 8).contiguous().float()
         nz = self.noise_override or {}
+        if torch.is_grad_enabled() and hasattr(model, "_wants_grad") and model._wants_grad(True):
+            return self._forward_train(model, rays.detach(), sb, want_weights, nz)
         with torch.no_grad():
             z_coarse = self.sample_coarse(rays, nz.get("coarse"))
             out_c = self._field(model, rays, z_coarse, True, sb)
@@ -154,6 +234,33 @@ class NeRFRenderer(torch.nn.Module):
                 out_f = self._field(model, rays, z_all, False, sb)
                 fine = self.composite_values(out_f, z_all, rays, want_weights=want_weights)
                 outputs.fine = self._format_outputs(fine, sb, want_weights)
+        return outputs
+
+    def _forward_train(self, model, rays, sb, want_weights, nz):
+        """The same sequence recorded for backward (PixelNerfTrainer.calc_losses -> loss.backward(), config 3):
+        every stage is an autograd.Function over the C-ABI forward/backward kernels."""
+        dev = rays.device
+        B = rays.shape[0]
+        with torch.no_grad():
+            z_coarse = self.sample_coarse(rays, nz.get("coarse"))
+        out_c = self._field(model, rays, z_coarse, True, sb)
+        w_c, rgb_c, depth_c = _CompositeFn.apply(out_c, z_coarse, rays, self.white_bkgd)
+        outputs = DotMap(coarse=self._format_outputs((w_c, rgb_c, depth_c), sb, want_weights))
+        if self.using_fine:
+            kf, kfd = self.n_fine - self.n_fine_depth, self.n_fine_depth
+            u, jitter, gauss = nz.get("fine_u"), nz.get("fine_jitter"), nz.get("depth")
+            if kf > 0:
+                if u is None:
+                    u = torch.rand(B, kf, dtype=torch.float32, device=dev)
+                if jitter is None:
+                    jitter = torch.rand_like(u)
+            if kfd > 0 and gauss is None:
+                gauss = torch.randn(B, kfd, dtype=torch.float32, device=dev)
+            z_all = _ResampleFn.apply(depth_c, w_c.detach(), rays, z_coarse, u, jitter, gauss, kf, kfd, self.depth_std,
+                                      self.lindisp)
+            out_f = self._field(model, rays, z_all, False, sb)
+            w_f, rgb_f, depth_f = _CompositeFn.apply(out_f, z_all, rays, self.white_bkgd)
+            outputs.fine = self._format_outputs((w_f, rgb_f, depth_f), sb, want_weights)
         return outputs
 
     def _format_outputs(self, rendered, sb, want_weights=False):

