@@ -45,7 +45,7 @@ constexpr int kTmemCols = 512;
 constexpr int kHCol = 256;
 constexpr int kMaxStages = 1024;
 
-struct Sched { int n_blocks, CL, n_linz, KBz; };
+struct Sched { int n_blocks, CL, n_linz, KBz, order; };   // order: (chunk, tile) pair order inside a layer, see fc_pair
 enum { MAT_LIN_IN = 0, MAT_LINZ = 1, MAT_FC0 = 2, MAT_FC1 = 3, MAT_LIN_OUT = 4 };
 struct Seg { int kind, blk, t, len; };
 struct StageSrc { int mat, blk, row0, k0; };   // row0 = first row of the 256-row slab
@@ -57,7 +57,17 @@ __host__ __device__ inline int sched_total(const Sched& s) {
 // stages [0, sched_pre) are the pre-combine part (run once per tile), the rest the post-combine part
 __host__ __device__ inline int sched_pre(const Sched& s) { return kMT + s.n_linz * kMT * s.KBz + s.CL * 32; }
 // per-tile stage order = MMA issue order:
-//   lin_in (2) | lin_z[0] | per block: fc_0 (K-chunk outer: kc(4) x mt(2) x kk(2)) | lin_z[b+1] | fc_1 (same) | lin_out (8)
+//   lin_in (2) | lin_z[0] | per block: fc_0 (8 (chunk, tile) pairs x kk(2), see fc_pair) | lin_z[b+1] | fc_1 (same) | lin_out (8)
+// Order of the (K-chunk kc, feature tile mt) pairs inside a 512x512 layer.  Chunks 0,1 come from the previous
+// layer's tile 0 and arrive first, so both output tiles consume them first; then tile 0 is finished (its
+// completion is signalled on its own barrier, so its epilogue overlaps the last two pairs), then tile 1.
+__host__ __device__ inline void fc_pair(int order, int t, int& kc, int& mt, int& kk) {
+  const int pr = t >> 1;                       // 0..7
+  kk = t & 1;
+  if (order == 0) { kc = pr >> 1; mt = pr & 1; return; }        // K-chunk outer: (c0,t0)(c0,t1)(c1,t0)...
+  kc = (pr < 4) ? (pr & 1) : (2 + (pr & 1));                    // (c0,t0)(c1,t0)(c0,t1)(c1,t1)(c2,t0)(c3,t0)(c2,t1)(c3,t1)
+  mt = (pr >> 1) & 1;
+}
 __host__ __device__ inline Seg walk_stage(const Sched& sc, int s) {
   Seg g;
   const int s1 = kMT * sc.KBz;
@@ -97,7 +107,7 @@ __host__ __device__ inline StageSrc decode_stage(const Sched& sc, int s) {
     case MAT_LIN_IN: r.row0 = g.t * 256; r.k0 = 0; break;
     case MAT_LINZ: { const ZPos z = z_position(sc.KBz, g.t); r.row0 = z.mt * 256; r.k0 = (z.pass * 8 + z.kbi) * 64; } break;
     case MAT_FC0:
-    case MAT_FC1: r.row0 = ((g.t % 4) / 2) * 256; r.k0 = (g.t / 4) * 128 + (g.t % 2) * 64; break;   // chunk kc=t/4, tile (t%4)/2, half t%2
+    case MAT_FC1: { int kc, mt, kk; fc_pair(sc.order, g.t, kc, mt, kk); r.row0 = mt * 256; r.k0 = kc * 128 + kk * 64; } break;
     default: r.row0 = 0; r.k0 = g.t * 64; break;
   }
   return r;
@@ -134,8 +144,9 @@ struct Smem {
   static constexpr uint32_t total = prog + 8 * kMaxStages;
 };
 enum {
-  B_W_FULL = 0, B_W_EMPTY = B_W_FULL + kStages, B_IN_READY = B_W_EMPTY + kStages, B_IN_FREE, B_X_FULL, B_H_FULL,
-  B_RDY, B_X_FREE = B_RDY + 4, B_COUNT
+  B_W_FULL = 0, B_W_EMPTY = B_W_FULL + kStages, B_IN_READY = B_W_EMPTY + kStages, B_IN_FREE,
+  B_X_FULL, B_H_FULL = B_X_FULL + kMT,          // one per feature tile
+  B_RDY = B_H_FULL + kMT, B_X_FREE = B_RDY + 4, B_COUNT
 };
 static_assert(B_COUNT <= 30, "barrier parity bits live in one 32-bit word");
 static_assert(Smem::total <= 227 * 1024, "shared memory budget");
@@ -143,7 +154,7 @@ static_assert(Smem::total <= 227 * 1024, "shared memory budget");
 struct ProgEntry { uint32_t w0, w1; };
 __device__ inline ProgEntry make_prog(const Sched& sc, int s, uint32_t sbase) {
   const Seg g = walk_stage(sc, s);
-  uint32_t b_addr = 0, dcol = 0, acc = 1, post = 0, wait_id = 0, c1 = 0, c2 = 0;
+  uint32_t b_addr = 0, dcol = 0, acc = 1, wait_id = 0, c1 = 0, c2 = 0, c3 = 0;
   const bool last = g.t == g.len - 1;
   switch (g.kind) {
     case MAT_LIN_IN:
@@ -157,33 +168,34 @@ __device__ inline ProgEntry make_prog(const Sched& sc, int s, uint32_t sbase) {
       b_addr = sbase + Smem::lat + z.kbi * kOperandKB; dcol = z.mt * 128;
       if (streaming && pass_first && !(g.blk == 0 && z.pass == 0)) wait_id = B_IN_READY + 1;
       if (pass_last && (streaming || g.blk == sc.n_linz - 1)) c1 = B_IN_FREE + 1;
-      if (last && g.blk == 0) c2 = B_X_FULL + 1;
+      if (last && g.blk == 0) { c2 = B_X_FULL + 1; c3 = B_X_FULL + 2; }
     } break;
-    case MAT_FC0: {
-      const int kc = g.t / 4, mt = (g.t % 4) / 2, kk = g.t % 2;
-      b_addr = sbase + Smem::ring + (kc * 2 + kk) * kOperandKB; dcol = kHCol + mt * 128; acc = (kc > 0 || kk > 0);
-      post = g.blk >= sc.CL;
-      if (g.t % 4 == 0) wait_id = B_RDY + kc + 1;
-      if (last) c2 = B_H_FULL + 1;
-    } break;
+    case MAT_FC0:
     case MAT_FC1: {
-      const int kc = g.t / 4, mt = (g.t % 4) / 2, kk = g.t % 2;
-      b_addr = sbase + Smem::ring + (kc * 2 + kk) * kOperandKB; dcol = mt * 128; post = g.blk >= sc.CL;
-      if (g.t % 4 == 0) wait_id = B_RDY + kc + 1;
-      if (last) c2 = B_X_FULL + 1;
+      int kc, mt, kk;
+      fc_pair(sc.order, g.t, kc, mt, kk);
+      const bool fc0 = g.kind == MAT_FC0;
+      b_addr = sbase + Smem::ring + (kc * 2 + kk) * kOperandKB; dcol = (fc0 ? kHCol : 0) + mt * 128;
+      if (fc0) acc = (kc > 0 || kk > 0);
+      if (mt == 0 && kk == 0) wait_id = B_RDY + kc + 1;          // first use of chunk kc (tile 0 precedes tile 1 for every chunk)
+      if (kc == 3 && kk == 1) c2 = (fc0 ? B_H_FULL : B_X_FULL) + mt + 1;   // tile mt complete
     } break;
     default: {
       const int kc = g.t / 2, kk = g.t % 2;
-      b_addr = sbase + Smem::ring + (kc * 2 + kk) * kOperandKB; dcol = kHCol; acc = g.t > 0; post = 1;
+      b_addr = sbase + Smem::ring + (kc * 2 + kk) * kOperandKB; dcol = kHCol; acc = g.t > 0;
       if (kk == 0) wait_id = B_RDY + kc + 1;
       if (last) c2 = B_H_FULL + 1;
     } break;
   }
   ProgEntry e;
-  e.w0 = ((b_addr >> 4) & 0x3FFFu) | (dcol << 14) | (acc << 23) | (post << 24) | (wait_id << 25);
-  e.w1 = c1 | (c2 << 5);
+  e.w0 = ((b_addr >> 4) & 0x3FFFu) | (dcol << 14) | (acc << 23) | (wait_id << 25);
+  e.w1 = c1 | (c2 << 5) | (c3 << 14);
   return e;
 }
+
+// Column i (< 16) of gather warp gw: at any time the four warps work on four adjacent columns = adjacent points of one
+// source view, whose 2x2 tap blocks overlap (their requests merge in L1).
+__device__ __forceinline__ int gather_col(int gw, int i) { return gw + kGatherWarps * i; }
 
 // Store an epilogue warp's [32 features x NC columns] block as operand rows (row = column, 16-byte chunk = 8 consecutive
 // features).  vals[c] = fp32 bits of this lane's feature at column c; bias/ReLU/bf16 rounding happen here.  Per 16
@@ -268,8 +280,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     for (int i = 0; i < kStages; ++i) { mbar_init(bar(B_W_FULL + i), 1); mbar_init(bar(B_W_EMPTY + i), 1); }
     mbar_init(bar(B_IN_READY), 2 * kGatherWarps);
     mbar_init(bar(B_IN_FREE), 1);
-    mbar_init(bar(B_X_FULL), 1);
-    mbar_init(bar(B_H_FULL), 1);
+    for (int i = 0; i < kMT; ++i) { mbar_init(bar(B_X_FULL + i), 1); mbar_init(bar(B_H_FULL + i), 1); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_RDY + i), kEpiWarps);
     mbar_init(bar(B_X_FREE), 2 * kEpiWarps);
     fence_barrier_init();
@@ -368,9 +379,10 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               const uint32_t d_col = (ecur.x >> 14) & 0x1FFu;
               mma_kblock_desc_2sm(tmem_base + d_col, wdesc0 + sl * kStageStep, b_desc, idesc, (ecur.x >> 23) & 1u);
               mma_commit_2sm(bar(B_W_EMPTY + sl), 3);
-              const uint32_t c1 = ecur.y & 31u, c2 = (ecur.y >> 5) & 31u;
+              const uint32_t c1 = ecur.y & 31u, c2 = (ecur.y >> 5) & 31u, c3 = (ecur.y >> 14) & 31u;
               if (c1) mma_commit_2sm(bar(c1 - 1), 3);
               if (c2) mma_commit_2sm(bar(c2 - 1), 3);
+              if (c3) mma_commit_2sm(bar(c3 - 1), 3);
               sl = sl + 1 == kStages ? 0 : sl + 1;
             }
           }
@@ -401,7 +413,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     auto wait = [&](int id) {
       PPROF_T0();
       mbar_wait_cluster(bar(id), (ph >> id) & 1u); ph ^= (1u << id); tc_fence_after();
-      if (prof_warp) PPROF_ADD(id == B_X_FULL ? 9 : 10);
+      if (prof_warp) PPROF_ADD(id < B_H_FULL ? 9 : 10);
     };
     const long long t_role0 = prof ? clock64() : 0;
     const uint32_t peer = crank ^ 1u;
@@ -425,8 +437,8 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       store_transposed<kNCol / 2, false, true>(loc, v, bias, lane, qd * 32, hs * (kNCol / 2));
     };
     auto x_epilogue = [&](int e) {                 // relu(x + cumulative bias) -> bf16 K-chunks
-      wait(B_X_FULL);
       for (int mt = 0; mt < kMT; ++mt) {
+        wait(B_X_FULL + mt);
         const int kc = 2 * mt + (int)crank;
         const float bias = bias_x[e * kHidden + mt * 256 + crank * 128 + fl];
         const long long ts0 = (prof && prof_warp) ? clock64() : 0;
@@ -436,8 +448,8 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       }
     };
     auto h_epilogue = [&](int b) {                 // relu(fc_0 out + b) -> bf16 K-chunks for fc_1
-      wait(B_H_FULL);
       for (int mt = 0; mt < kMT; ++mt) {
+        wait(B_H_FULL + mt);
         const int kc = 2 * mt + (int)crank;
         const float bias = bias_h[b * kHidden + mt * 256 + crank * 128 + fl];
         convert_unit(kHCol + mt * 128, kc, bias);
@@ -452,7 +464,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         const int obj = tile / tiles_per_obj;
         const int p0 = (tile - obj * tiles_per_obj) * PP;
         for (int e = 0; e < sch.CL; ++e) { x_epilogue(e); h_epilogue(e); }
-        wait(B_X_FULL);
+        for (int mt = 0; mt < kMT; ++mt) wait(B_X_FULL + mt);
         // view mean (combine_interleaved) + cumulative bias -> x-bar, column g*PP + p of slot hs
         for (int mt = 0; mt < kMT; ++mt) {
           const int f = mt * 256 + (int)crank * 128 + fl;
@@ -504,7 +516,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         if (e < sch.n_blocks) h_epilogue(e);
       }
       // ---- output: lin_out rows are features 0..d_out-1 -> leader CTA, TMEM lanes 0..d_out-1 of h tile 0
-      wait(B_H_FULL);
+      wait(B_H_FULL);                              // lin_out signals tile 0 only
       if (crank == 0 && qd == 0) {
         uint32_t r[kNCol];
         tmem_ld<kNCol>(tlane + kHCol + hs * kNCol, r);
@@ -551,7 +563,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       long long vbase = -1;                          // element offset of this lane's column's source view, -1 = dead column
       Projection pr;
       {
-        const int c = gw + kGatherWarps * (lane & 15);
+        const int c = gather_col(gw, lane & 15);
         const int v = c / PP, p = c - v * PP;
         const bool valid = (tile < n_tiles) && (v < NS) && (p0 + p < q.P);
         pr.xr = pr.yr = pr.zr = pr.dx = pr.dy = pr.dz = pr.ix = pr.iy = 0.f;
@@ -576,10 +588,10 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         const int j0 = lane * 2, d_in = 6 * num_freqs + 6;
         float a = 0.f, b = 0.f;
         if (vi) {
-          if (j0 < d_in) a = zfeat_value(pi, j0, num_freqs, freq_factor);
-          if (j0 + 1 < d_in) b = zfeat_value(pi, j0 + 1, num_freqs, freq_factor);
+          if (j0 < d_in) a = zfeat_value_fast(pi, j0, num_freqs, freq_factor);
+          if (j0 + 1 < d_in) b = zfeat_value_fast(pi, j0 + 1, num_freqs, freq_factor);
         }
-        *reinterpret_cast<__nv_bfloat162*>(smem + Smem::zf + swz_offset(gw + kGatherWarps * i, j0)) = __floats2bfloat162_rn(a, b);
+        *reinterpret_cast<__nv_bfloat162*>(smem + Smem::zf + swz_offset(gather_col(gw, i), j0)) = __floats2bfloat162_rn(a, b);
       };
       for (int fill = 0; fill < fills; ++fill) {
         const int pass = fill % n_pass;
@@ -633,7 +645,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
             q0[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
             q1[j] = __floats2bfloat162_rn(acc[8 + 2 * j], acc[8 + 2 * j + 1]);
           }
-          const int c = gw + kGatherWarps * i;
+          const int c = gather_col(gw, i);
           uint8_t* kb_base = smem + Smem::lat + (lane >> 2) * kOperandKB;
           const int k_in = (lane & 3) * 16;
           *reinterpret_cast<uint4*>(kb_base + swz_offset(c, k_in)) = o0;
@@ -643,14 +655,17 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           uint4 ra[8], rb[8];
           float wa[4], wb[4];
           load_col(0, ra, wa);
+          load_col(1, rb, wb);
+          if (fill == 0) {                           // the sin/cos work runs under the first loads' latency
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) zfeat_col(i);
+          }
 #pragma unroll 1
           for (int i = 0; i < 16; i += 2) {
-            load_col(i + 1, rb, wb);
-            if (fill == 0) zfeat_col(i);             // sin/cos work hides part of the load latency
             blend_col(i, ra, wa);
             if (i + 2 < 16) load_col(i + 2, ra, wa);
-            if (fill == 0) zfeat_col(i + 1);
             blend_col(i + 1, rb, wb);
+            if (i + 3 < 16) load_col(i + 3, rb, wb);
           }
         }
         fence_proxy_async();                 // the gather writes this CTA's own shared memory only
@@ -671,16 +686,22 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
 }  // namespace pair
 
 // ---- host side ---------------------------------------------------------------------------------------------
+// PNR_ORDER=0 selects the K-chunk-outer pair order (experiments); default 1.  Read once: pack and launch must agree.
+static int pair_order() {
+  static int cached = -1;
+  if (cached < 0) { const char* e = getenv("PNR_ORDER"); cached = (e && atoi(e) == 0) ? 0 : 1; }
+  return cached;
+}
 size_t pair_stream_bytes(const pnr_mlp_params* p) {
-  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64};
+  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64, pair_order()};
   return (size_t)pair::sched_total(s) * 2 * kStageBytes;
 }
 int pair_stages(const pnr_mlp_params* p) {
-  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64};
+  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64, pair_order()};
   return pair::sched_total(s);
 }
 int pair_pack(const pnr_mlp_params* p, uint8_t* stream, cudaStream_t st) {
-  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64};
+  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64, pair_order()};
   PNR_REQUIRE(pair::sched_total(s) <= pair::kMaxStages, PNR_ERR_UNSUPPORTED, "pair_pack: %d stages exceed the stage program", pair::sched_total(s));
   pair::pack_stages_kernel<<<pair::sched_total(s) * 2, 256, 0, st>>>(*p, s, stream);
   PNR_CHECK_LAUNCH("pair::pack_stages_kernel");
@@ -702,7 +723,7 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
               "field_forward_pair: workspace of pnr_field_workspace_bytes() = %zu bytes required (got %zu)",
               pair_workspace_bytes(), ws_bytes);
   float* xbar = (float*)ws;
-  pair::Sched sch{mp->n_blocks, mp->combine_layer, mp->combine_layer, mp->d_latent / 64};
+  pair::Sched sch{mp->n_blocks, mp->combine_layer, mp->combine_layer, mp->d_latent / 64, pair_order()};
   const int PP = pair::kNCol / sc->NS;
   const int tiles_per_obj = (q->P + PP - 1) / PP;
   const long long n_tiles_ll = (long long)tiles_per_obj * sc->SB;

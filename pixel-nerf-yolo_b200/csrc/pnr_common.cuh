@@ -110,6 +110,24 @@ __device__ __forceinline__ float zfeat_value(const Projection& p, int j, int num
   return d == 0 ? p.dx : (d == 1 ? p.dy : p.dz);
 }
 
+// Same element for the bf16 tensor-core path, where the value is rounded to bf16 (2^-9 relative) right after: explicit
+// range reduction in turns + the SFU sine (abs error < 1e-5 for |f x| < 128) instead of the ~40-instruction libm sinf,
+// which was 45 % of the gather warps' issue slots in the fused kernel (ncu source page, profiles/).
+__device__ __forceinline__ float zfeat_value_fast(const Projection& p, int j, int num_freqs, float freq_factor) {
+  const int n_pe = 3 + 6 * num_freqs;
+  if (j < 3) return j == 0 ? p.xr : (j == 1 ? p.yr : p.zr);
+  if (j < n_pe) {
+    const int q = j - 3, k = q / 6, r = q - k * 6, d = r % 3;
+    const float x = d == 0 ? p.xr : (d == 1 ? p.yr : p.zr);
+    const float f_turns = freq_factor * (float)(1 << k) * 0.15915494309189535f;      // f / (2 pi)
+    float t = fmaf(x, f_turns, r >= 3 ? 0.25f : 0.0f);
+    t -= rintf(t);                                                                    // [-0.5, 0.5] turns
+    return __sinf(t * 6.283185307179586f);
+  }
+  const int d = j - n_pe;
+  return d == 0 ? p.dx : (d == 1 ? p.dy : p.dz);
+}
+
 // Fetch world point + direction `idx` (flattened (object, point)) from either point source.
 __device__ __forceinline__ void fetch_point(const pnr_points& q, long long idx, float& px, float& py,
                                             float& pz, float& vx, float& vy, float& vz) {
