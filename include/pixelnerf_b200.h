@@ -94,6 +94,19 @@ int pnr_sample_fine(const float* weights, const float* depth, const float* rays,
 /* src (N, C, H, W) fp32 -> dst (N, H, W, C) bf16 (to_fp32=0) or fp32 (to_fp32=1). */
 int pnr_pack_features(const float* src, void* dst, int N, int C, int H, int W, int to_fp32, void* stream);
 
+/* SpatialEncoder.forward's tail in one pass (src/model/encoder.py:159-168): every pyramid level (N, C_l, H_l, W_l) fp32 is
+ * upsampled bilinearly (align_corners=True) to level 0's size, concatenated along channels and written channels-last:
+ * dst (N, H_0, W_0, sum C_l) bf16 (to_fp32=0) or fp32.  `levels` is a HOST array of n_levels (<= 8) device pointers. */
+int pnr_pyramid_pack(const float* const* levels, const int32_t* level_C, const int32_t* level_H, const int32_t* level_W,
+                     int n_levels, int N, void* dst, int to_fp32, void* stream);
+
+/* ---- ray generation (src/util/util.py:115-145 unproj_map, 240-278 gen_rays) --------------------------------- */
+/* poses (N, 4, 4) camera-to-world -> rays [origin(3), dir(3), near, far].  pix_inds == NULL: all N*H*W pixels, rays
+ * (N, H, W, 8), n_out = N*H*W.  Otherwise pix_inds (n_out) int64 flat indices into (N, H, W) (the trainer's ray
+ * sampling, PixelNerfTrainer.py:100-117) and rays (n_out, 8). */
+int pnr_gen_rays(const float* poses, const long long* pix_inds, float* rays, long long n_out, int N, int H, int W,
+                 float fx, float fy, float cx, float cy, float z_near, float z_far, void* stream);
+
 /* ---- project + 4-tap gather + positional encoding, stand-alone ---------------------------------- */
 /* models.py:168-230 + encoder.py:79-108 + code.py:30-42.  For every (object, view, point) row
  * r = (s*NS + v)*P + p writes latent_out[r, 0:C] (bf16 if out_fp32=0 else fp32) and zfeat_out[r, 0:42]

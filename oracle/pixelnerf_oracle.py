@@ -354,3 +354,38 @@ def render(scene: Scene, mlp_coarse: Dict[str, torch.Tensor], mlp_fine: Optional
             res["fine"] = dict(rgb=rgbf.reshape(SB, -1, 3), depth=df.reshape(SB, -1),
                                weights=wf.reshape(SB, -1, wf.shape[-1]), z=z_all)
     return res
+
+
+# --------------------------------------------------------------------------- #
+# the steps either side of the path
+# --------------------------------------------------------------------------- #
+def pyramid_latent(levels, upsample_interp: str = "bilinear") -> torch.Tensor:
+    """SpatialEncoder.forward's tail (encoder.py:159-168): upsample every level to the first level's size
+    (align_corners=True) and concatenate along channels -> latent (N, sum C_l, H_0, W_0)."""
+    size = levels[0].shape[-2:]
+    ups = [torch.nn.functional.interpolate(l, size, mode=upsample_interp, align_corners=True) for l in levels]
+    return torch.cat(ups, dim=1)
+
+
+def unproj_map(width: int, height: int, f, c=None) -> torch.Tensor:
+    """util.py:115-145: unit camera ray per pixel, (H, W, 3)."""
+    if c is None:
+        c = [width * 0.5, height * 0.5]
+    f = [float(f), float(f)] if not hasattr(f, "__len__") else [float(f[0]), float(f[-1])]
+    Y, X = torch.meshgrid(torch.arange(height, dtype=torch.float32) - float(c[1]),
+                          torch.arange(width, dtype=torch.float32) - float(c[0]), indexing="ij")
+    X = X / f[0]
+    Y = Y / f[1]
+    unproj = torch.stack((X, -Y, -torch.ones_like(X)), dim=-1)
+    return unproj / torch.norm(unproj, dim=-1).unsqueeze(-1)
+
+
+def gen_rays(poses: torch.Tensor, width: int, height: int, focal, z_near: float, z_far: float, c=None) -> torch.Tensor:
+    """util.py:240-278 (ndc=False): (N, H, W, 8) = [camera centre, R d, near, far]."""
+    n = poses.shape[0]
+    um = unproj_map(width, height, focal, c).unsqueeze(0).repeat(n, 1, 1, 1)
+    centers = poses[:, None, None, :3, 3].expand(-1, height, width, -1)
+    dirs = torch.matmul(poses[:, None, None, :3, :3], um.unsqueeze(-1))[:, :, :, :, 0]
+    near = torch.tensor(z_near).view(1, 1, 1, 1).expand(n, height, width, -1)
+    far = torch.tensor(z_far).view(1, 1, 1, 1).expand(n, height, width, -1)
+    return torch.cat((centers, dirs, near, far), dim=-1)

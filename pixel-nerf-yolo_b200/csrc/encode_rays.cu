@@ -1,0 +1,141 @@
+// The two steps either side of the rendering hot path:
+//   * pnr_pyramid_pack: SpatialEncoder.forward's tail (src/model/encoder.py:159-168) -- bilinear upsampling
+//     (align_corners=True) of every pyramid level to the first level's size, channel concat, and the repack the hot
+//     path wants (NCHW fp32 -> channels-last bf16/fp32) -- in ONE pass: the fp32 NCHW `latent` (25 MB at 128^2,
+//     629 MB at 640^2) is never materialised, each level is read once and the channels-last maps are written once.
+//   * pnr_gen_rays: util.gen_rays / util.unproj_map (src/util/util.py:115-145, 240-278) -- per-pixel camera ray
+//     [origin, direction, near, far], optionally only for a list of selected pixels (the trainer's ray sampling,
+//     train/trainlib/PixelNerfTrainer.py:100-117).
+// Both are HBM-bound streaming kernels: coalesced loads along W of the source level, a shared-memory transpose, and
+// 16-byte channels-last stores.
+#include "pnr_common.cuh"
+
+namespace pnr {
+
+struct PyramidLevels {
+  const float* src[8];     // (N, C_l, H_l, W_l) fp32
+  int C[8], H[8], W[8];
+  int c0[8];               // first output channel of the level
+  int n_levels;
+};
+
+// Block = 32 output pixels of one row (x0..x0+31) x 32 channels of one level; threads (32, 8).
+// Phase 1: thread (tx, ty) computes channel c = cb + ty + 8 r at pixel x0 + tx (source reads coalesced along W).
+// Phase 2: transposed write, lane -> channel, so the channels-last store is contiguous.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+pyramid_pack_kernel(const PyramidLevels lv, OutT* __restrict__ dst, int Ho, int Wo, int Ctot) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int y = blockIdx.y;
+  // blockIdx.x enumerates (level, channel block, x block)
+  int rem = blockIdx.x, l = 0;
+  const int xblocks = (Wo + 31) / 32;
+  for (; l < lv.n_levels; ++l) {
+    const int nb = ((lv.C[l] + 31) / 32) * xblocks;
+    if (rem < nb) break;
+    rem -= nb;
+  }
+  const int cb = (rem / xblocks) * 32, x0 = (rem % xblocks) * 32;
+  const int Hl = lv.H[l], Wl = lv.W[l], Cl = lv.C[l];
+  const float* src = lv.src[l] + (size_t)n * Cl * Hl * Wl;
+  // F.interpolate(mode="bilinear", align_corners=True): src = dst * (in - 1) / (out - 1)       (ATen UpSample.h)
+  const float sy = Ho > 1 ? (float)(Hl - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(Wl - 1) / (float)(Wo - 1) : 0.f;
+  const float fy = sy * (float)y;
+  const int y0 = (int)fy;
+  const int y1 = y0 + (y0 < Hl - 1 ? 1 : 0);
+  const float ly = fy - (float)y0;
+  const int x = x0 + threadIdx.x;
+  const float fx = sx * (float)x;
+  const int xa = (int)fx;
+  const int xb = xa + (xa < Wl - 1 ? 1 : 0);
+  const float lx = fx - (float)xa;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = cb + r;
+    float v = 0.f;
+    if (c < Cl && x < Wo) {
+      const float* p = src + (size_t)c * Hl * Wl;
+      const float a = p[y0 * Wl + xa], b = p[y0 * Wl + xb], cc = p[y1 * Wl + xa], d = p[y1 * Wl + xb];
+      v = (1.f - ly) * ((1.f - lx) * a + lx * b) + ly * ((1.f - lx) * cc + lx * d);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int xo = x0 + r, c = cb + threadIdx.x;
+    if (xo < Wo && c < Cl) {
+      const float v = tile[threadIdx.x][r];
+      const size_t o = (((size_t)n * Ho + y) * Wo + xo) * Ctot + lv.c0[l] + c;
+      if constexpr (sizeof(OutT) == 2) dst[o] = __float2bfloat16_rn(v);
+      else dst[o] = v;
+    }
+  }
+}
+
+// util.py:115-145 + 240-278.  One thread per output ray.
+__global__ void gen_rays_kernel(const float* __restrict__ poses, const long long* __restrict__ pix_inds,
+                                float* __restrict__ rays, long long n_out, int N, int H, int W, float fx, float fy,
+                                float cx, float cy, float z_near, float z_far) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const long long pix = pix_inds ? pix_inds[i] : i;          // flat index into (N, H, W)
+  const int n = (int)(pix / ((long long)H * W));
+  const int yx = (int)(pix - (long long)n * H * W);
+  const int y = yx / W, x = yx - y * W;
+  // unproj_map: X = (x - cx) / fx, Y = (y - cy) / fy, d = (X, -Y, -1) / |d|
+  const float X = __fdiv_rn(__fsub_rn((float)x, cx), fx);
+  const float Y = __fdiv_rn(__fsub_rn((float)y, cy), fy);
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(X, X), __fmul_rn(Y, Y)), 1.0f));
+  const float dx = __fdiv_rn(X, nrm), dy = __fdiv_rn(-Y, nrm), dz = __fdiv_rn(-1.0f, nrm);
+  const float* P = poses + (size_t)n * 16;                  // camera-to-world (4, 4)
+  float* o = rays + i * 8;
+  o[0] = P[3]; o[1] = P[7]; o[2] = P[11];
+  o[3] = P[0] * dx + P[1] * dy + P[2] * dz;                 // R d
+  o[4] = P[4] * dx + P[5] * dy + P[6] * dz;
+  o[5] = P[8] * dx + P[9] * dy + P[10] * dz;
+  o[6] = z_near; o[7] = z_far;
+}
+
+}  // namespace pnr
+
+using namespace pnr;
+
+extern "C" int pnr_pyramid_pack(const float* const* levels, const int32_t* level_C, const int32_t* level_H,
+                                const int32_t* level_W, int n_levels, int N, void* dst, int to_fp32, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(levels && level_C && level_H && level_W && dst, PNR_ERR_ARG, "pnr_pyramid_pack: null pointer");
+  PNR_REQUIRE(n_levels >= 1 && n_levels <= 8 && N >= 1 && N <= 65535, PNR_ERR_ARG, "pnr_pyramid_pack: bad level/map count");
+  PyramidLevels lv = {};
+  lv.n_levels = n_levels;
+  int ctot = 0;
+  long long blocks = 0;
+  const int Ho = level_H[0], Wo = level_W[0];
+  PNR_REQUIRE(Ho >= 1 && Wo >= 1 && Ho <= 65535, PNR_ERR_ARG, "pnr_pyramid_pack: bad output size");
+  for (int l = 0; l < n_levels; ++l) {
+    PNR_REQUIRE(levels[l] && level_C[l] > 0 && level_H[l] > 0 && level_W[l] > 0, PNR_ERR_ARG, "pnr_pyramid_pack: bad level %d", l);
+    lv.src[l] = levels[l]; lv.C[l] = level_C[l]; lv.H[l] = level_H[l]; lv.W[l] = level_W[l]; lv.c0[l] = ctot;
+    ctot += level_C[l];
+    blocks += (long long)((level_C[l] + 31) / 32) * ((Wo + 31) / 32);
+  }
+  PNR_REQUIRE(blocks < (1LL << 31), PNR_ERR_ARG, "pnr_pyramid_pack: too many blocks");
+  dim3 grid((unsigned)blocks, (unsigned)Ho, (unsigned)N), block(32, 8);
+  if (to_fp32) pyramid_pack_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(lv, (float*)dst, Ho, Wo, ctot);
+  else pyramid_pack_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(lv, (__nv_bfloat16*)dst, Ho, Wo, ctot);
+  PNR_CHECK_LAUNCH("pyramid_pack_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_gen_rays(const float* poses, const long long* pix_inds, float* rays, long long n_out, int N, int H,
+                            int W, float fx, float fy, float cx, float cy, float z_near, float z_far, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(poses && rays, PNR_ERR_ARG, "pnr_gen_rays: null pointer");
+  PNR_REQUIRE(N >= 1 && H >= 1 && W >= 1 && n_out >= 0, PNR_ERR_ARG, "pnr_gen_rays: bad shape");
+  PNR_REQUIRE(pix_inds || n_out == (long long)N * H * W, PNR_ERR_ARG, "pnr_gen_rays: n_out must be N*H*W without pix_inds");
+  PNR_REQUIRE(fx != 0.f && fy != 0.f, PNR_ERR_ARG, "pnr_gen_rays: zero focal length");
+  if (n_out == 0) return PNR_OK;
+  gen_rays_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, pix_inds, rays, n_out, N, H, W, fx,
+                                                                                    fy, cx, cy, z_near, z_far);
+  PNR_CHECK_LAUNCH("gen_rays_kernel");
+  return PNR_OK;
+}

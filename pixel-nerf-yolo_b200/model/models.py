@@ -143,7 +143,7 @@ class PixelNeRFNet(torch.nn.Module):
             poses = poses.reshape(-1, 4, 4)
         else:
             self.num_views_per_obj = 1
-        self.encoder(images)
+        self.encoder(images, return_latent=False)
         self.set_cameras(poses, focal, (images.shape[-1], images.shape[-2]), c)
 
     def set_cameras(self, poses, focal, image_wh, c=None):

@@ -1,0 +1,50 @@
+"""Ray generation: drop-in for ``util.gen_rays`` / ``util.unproj_map`` (src/util/util.py:115-145, 240-278), the step
+right before the renderer, as one kernel of the C-ABI library (``pnr_gen_rays``).
+
+``pix_inds`` is an extension for the trainer's ray sampling (PixelNerfTrainer.py:100-117): instead of generating all
+N*H*W rays and indexing them, only the selected pixels' rays are produced.
+"""
+import warnings
+
+import torch
+
+from . import _lib
+
+
+def _pair(v, default=None):
+    if v is None:
+        return default
+    if isinstance(v, (int, float)):
+        return float(v), float(v)
+    v = torch.as_tensor(v).detach().float().reshape(-1).cpu()
+    return (float(v[0]), float(v[0])) if v.numel() == 1 else (float(v[0]), float(v[1]))
+
+
+def gen_rays(poses, width, height, focal, z_near, z_far, c=None, ndc=False, pix_inds=None):
+    """poses (N, 4, 4) camera-to-world on a CUDA device -> rays (N, H, W, 8) = [origin, direction, near, far]
+    (or (len(pix_inds), 8) for flat pixel indices into (N, H, W))."""
+    if ndc:
+        raise NotImplementedError("gen_rays (B200 path): ndc rays are not built (no shipped conf renders in NDC)")
+    _lib.require_cuda(poses, "poses")
+    _lib.require_device(poses.device)
+    dev = poses.device
+    n = poses.shape[0]
+    fx, fy = _pair(focal.squeeze() if torch.is_tensor(focal) else focal)
+    cx, cy = _pair(c.squeeze() if torch.is_tensor(c) else c, (width * 0.5, height * 0.5))
+    p = poses.detach().contiguous().float()
+    if pix_inds is None:
+        n_out = n * height * width
+        rays = torch.empty(n, height, width, 8, device=dev, dtype=torch.float32)
+        idx_ptr = None
+    else:
+        pix_inds = pix_inds.to(device=dev, dtype=torch.int64).contiguous()
+        n_out = pix_inds.numel()
+        rays = torch.empty(n_out, 8, device=dev, dtype=torch.float32)
+        if n_out == 0:
+            return rays
+        idx_ptr = pix_inds.data_ptr()
+    with torch.cuda.device(dev):
+        rc = _lib.load().pnr_gen_rays(p.data_ptr(), idx_ptr, rays.data_ptr(), n_out, n, height, width, fx, fy, cx, cy,
+                                      float(z_near), float(z_far), _lib.stream_ptr(dev))
+    _lib.check(rc, "pnr_gen_rays")
+    return rays
