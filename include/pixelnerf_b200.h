@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PNR_ABI_VERSION 1
+#define PNR_ABI_VERSION 2
 
 /* precision of the field function (PixelNeRFNet.forward) */
 #define PNR_PREC_FP32 0 /* SIMT fp32 operands + fp32 accumulate: the <=1e-4 "accumulate-only" check build */
@@ -51,7 +51,16 @@ typedef struct pnr_scene {
   int32_t feat_fp32;   /* 0: bf16 maps, 1: fp32 maps                                                */
   float image_w, image_h;          /* PixelNeRFNet.image_shape  models.py:122-123                   */
   float lat_scale_x, lat_scale_y;  /* SpatialEncoder.latent_scaling  encoder.py:170-172             */
+  int32_t flags;       /* PNR_SCENE_* bits                                                          */
 } pnr_scene;
+
+/* YOLO mode of PixelNeRFNet.forward (models.py:221-224, 254-264): the latent of a (point, view) row is zeroed where the
+ * point's camera-space z is >= 0.  (The mode's other differences are data: poses are used as given and the focal
+ * signs differ, models.py:119-120,136-137,220-222 -- the caller passes focal with the sign that makes
+ * uv = -xy / z * focal + c come out right.) */
+#define PNR_SCENE_MASK_NONNEG_Z 1
+/* pnr_field_forward returns the raw lin_out values instead of [sigmoid(rgb), relu(sigma)] (models.py:309-310). */
+#define PNR_SCENE_RAW_OUTPUT 2
 
 /* Where the query points of a field evaluation come from. */
 typedef struct pnr_points {
@@ -89,6 +98,10 @@ int pnr_sample_fine(const float* weights, const float* depth, const float* rays,
                     const float* u, const float* jitter, const float* gauss, float* z_out,
                     int32_t* inds_out, float* z_fine_out, float* z_depth_out, int B, int Kc, int Kf,
                     int Kfd, float depth_std, int lindisp, void* stream);
+
+/* YoloRenderer.forward's per-ray reduction (src/render/yolo.py:96-114): raw field values out (B, K, A*7) ->
+ * result (B, A, 7) = [max_k p, sum_k(v p) / (sum_k p + 1e-5)], p = sigmoid(first value of the anchor). */
+int pnr_yolo_reduce(const float* out, float* result, int B, int K, int num_anchors, void* stream);
 
 /* ---- encode-side repack (SpatialEncoder.latent NCHW fp32 -> channels-last) ---------------------- */
 /* src (N, C, H, W) fp32 -> dst (N, H, W, C) bf16 (to_fp32=0) or fp32 (to_fp32=1). */

@@ -99,8 +99,9 @@ class Scene:
 # --------------------------------------------------------------------------- #
 def encode_cameras(latent: torch.Tensor, poses_c2w: torch.Tensor, focal: torch.Tensor,
                    image_wh: Tuple[int, int], c: Optional[torch.Tensor] = None,
-                   num_views: Optional[int] = None) -> Scene:
-    """models.py:92-151 minus ``self.encoder(images)``; ``latent`` is the encoder output."""
+                   num_views: Optional[int] = None, yolo: bool = False) -> Scene:
+    """models.py:92-151 minus ``self.encoder(images)``; ``latent`` is the encoder output.
+    ``yolo``: poses are used as given and fy keeps its sign (models.py:119-120, 136-137)."""
     if poses_c2w.dim() == 4:  # (SB, NS, 4, 4)
         num_views = poses_c2w.shape[1]
         poses_c2w = poses_c2w.reshape(-1, 4, 4)
@@ -109,6 +110,8 @@ def encode_cameras(latent: torch.Tensor, poses_c2w: torch.Tensor, focal: torch.T
     rot = poses_c2w[:, :3, :3].transpose(1, 2)              # models.py:116
     trans = -torch.bmm(rot, poses_c2w[:, :3, 3:])           # models.py:117
     w2c = torch.cat((rot, trans), dim=-1)                   # models.py:118
+    if yolo:
+        w2c = poses_c2w[:, :3, :4]                          # models.py:120
     image_shape = torch.tensor([float(image_wh[0]), float(image_wh[1])])  # models.py:122-123
     focal = torch.as_tensor(focal, dtype=torch.float32)
     if focal.dim() == 0:                                    # models.py:126-134
@@ -118,7 +121,8 @@ def encode_cameras(latent: torch.Tensor, poses_c2w: torch.Tensor, focal: torch.T
     else:
         focal = focal.clone()
     focal = focal.float()
-    focal[..., 1] *= -1.0                                   # models.py:137
+    if not yolo:
+        focal[..., 1] *= -1.0                               # models.py:137
     if c is None:                                           # models.py:139-148
         c = (image_shape * 0.5).unsqueeze(0)
     else:
@@ -221,7 +225,7 @@ def resnetfc_forward(p: Dict[str, torch.Tensor], zx: torch.Tensor, d_latent: int
 def field_forward(scene: Scene, mlp: Dict[str, torch.Tensor], xyz: torch.Tensor,
                   viewdirs: torch.Tensor, *, num_freqs: int = 6, freq_factor: float = 1.5,
                   n_blocks: int = 5, combine_layer: int = 3, padding: str = "zeros",
-                  return_raw: bool = False) -> torch.Tensor:
+                  return_raw: bool = False, yolo: bool = False) -> torch.Tensor:
     """PixelNeRFNet.forward (models.py:153-318) for the default_mv.conf switches
     (use_xyz, normalize_z, use_code, not use_code_viewdirs, use_viewdirs, no global encoder).
     xyz, viewdirs (SB, P, 3) -> (SB, P, 4) = [sigmoid rgb, relu sigma]."""
@@ -236,7 +240,10 @@ def field_forward(scene: Scene, mlp: Dict[str, torch.Tensor], xyz: torch.Tensor,
     vd = rep(viewdirs.reshape(SB, P, 3, 1))
     vd = torch.matmul(R, vd).reshape(-1, 3)                                 # models.py:201-206
     zf = torch.cat((zf, vd), dim=1)                                         # models.py:207-209
-    uv = -x_cam[:, :, :2] / x_cam[:, :, 2:]                                 # models.py:220
+    if not yolo:
+        uv = -x_cam[:, :, :2] / x_cam[:, :, 2:]                             # models.py:220
+    else:
+        uv = x_cam[:, :, :2] / x_cam[:, :, 2:]                              # models.py:222
     foc = scene.focal.unsqueeze(1)
     cc = scene.c.unsqueeze(1)
     if foc.shape[0] > 1:                                                    # models.py:225-227
@@ -247,10 +254,13 @@ def field_forward(scene: Scene, mlp: Dict[str, torch.Tensor], xyz: torch.Tensor,
     lat = bilinear_index(scene.latent, uv, scene.latent_scaling, scene.image_shape, padding)
     C = lat.shape[1]
     lat = lat.transpose(1, 2).reshape(-1, C)                                # models.py:244-246
+    if yolo:                                                                # models.py:223, 254-264
+        nonneg = (x_cam[:, :, 2:] >= 0).reshape(-1, 1)
+        lat = torch.where(nonneg | lat.isnan(), torch.zeros_like(lat), lat)
     mlp_in = torch.cat((lat, zf), dim=-1)                                   # models.py:276
     out = resnetfc_forward(mlp, mlp_in, C, n_blocks, combine_layer, (NS, P))
     out = out.reshape(-1, P, out.shape[-1])
-    if return_raw:
+    if return_raw or yolo:                                                  # models.py:309-310
         return out.reshape(SB, P, -1)
     rgb = _f64(torch.sigmoid, out[..., :3])                                 # models.py:312-317
     sigma = torch.relu(out[..., 3:4])
@@ -389,3 +399,20 @@ def gen_rays(poses: torch.Tensor, width: int, height: int, focal, z_near: float,
     near = torch.tensor(z_near).view(1, 1, 1, 1).expand(n, height, width, -1)
     far = torch.tensor(z_far).view(1, 1, 1, 1).expand(n, height, width, -1)
     return torch.cat((centers, dirs, near, far), dim=-1)
+
+
+def yolo_render(scene: Scene, mlp: Dict[str, torch.Tensor], rays: torch.Tensor, noise: torch.Tensor, *,
+                n_coarse: int = 128, num_anchors: int = 3, **field_kw) -> torch.Tensor:
+    """YoloRenderer.forward (src/render/yolo.py:37-114).  rays (B, 8), noise (B, Kc) -> (B, anchors, 7)."""
+    with torch.no_grad():
+        r = rays.reshape(-1, 8)
+        z = sample_coarse(r, noise, n_coarse, False)                        # yolo.py:15-27
+        B, K = z.shape
+        pts, dirs = ray_points(r, z)                                        # yolo.py:58-66
+        out = field_forward(scene, mlp, pts.reshape(1, -1, 3), dirs.reshape(1, -1, 3), yolo=True, **field_kw)
+        out = out.reshape(B, K, num_anchors, 7)                             # yolo.py:93
+        prob = _f64(torch.sigmoid, out[..., 0])                             # yolo.py:96
+        summed = prob.sum(dim=1)
+        vals = (out[..., 1:] * prob.unsqueeze(-1)).sum(dim=1)
+        vals = vals / (summed.unsqueeze(-1) + 1e-5)                         # yolo.py:107
+        return torch.cat([prob.max(dim=1)[0].unsqueeze(-1), vals], dim=-1)  # yolo.py:109-114

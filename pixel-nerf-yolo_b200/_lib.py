@@ -17,6 +17,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpixelnerf_b200.so")
 
 PREC_FP32 = 0
 PREC_BF16 = 1
+SCENE_MASK_NONNEG_Z = 1
+SCENE_RAW_OUTPUT = 2
 
 # every symbol include/pixelnerf_b200.h declares
 EXPORTS = [
@@ -26,7 +28,7 @@ EXPORTS = [
     "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
     "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench",
     "pnr_field_tape_bytes", "pnr_field_forward_train", "pnr_field_backward_workspace_bytes", "pnr_field_backward",
-    "pnr_composite_backward", "pnr_sample_fine_depth_backward", "pnr_pyramid_pack", "pnr_gen_rays",
+    "pnr_composite_backward", "pnr_sample_fine_depth_backward", "pnr_pyramid_pack", "pnr_gen_rays", "pnr_yolo_reduce",
 ]
 
 
@@ -34,7 +36,7 @@ class Scene(C.Structure):
     _fields_ = [("feat", C.c_void_p), ("poses", C.c_void_p), ("focal", C.c_void_p), ("center", C.c_void_p),
                 ("SB", C.c_int32), ("NS", C.c_int32), ("C", C.c_int32), ("Hl", C.c_int32), ("Wl", C.c_int32),
                 ("feat_fp32", C.c_int32), ("image_w", C.c_float), ("image_h", C.c_float),
-                ("lat_scale_x", C.c_float), ("lat_scale_y", C.c_float)]
+                ("lat_scale_x", C.c_float), ("lat_scale_y", C.c_float), ("flags", C.c_int32)]
 
 
 class Points(C.Structure):
@@ -115,11 +117,12 @@ def load() -> C.CDLL:
     lib.pnr_sample_fine_depth_backward.argtypes = [vp] * 6 + [i32, i32, i32, f32, vp]
     lib.pnr_pyramid_pack.argtypes = [C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      i32, i32, vp, i32, vp]
+    lib.pnr_yolo_reduce.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.pnr_gen_rays.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, f32, f32, f32, f32, f32, f32, vp]
     for name in EXPORTS:
         getattr(lib, name)          # AttributeError here = header and library disagree
-    if lib.pnr_version() != 1:
-        raise NativeLibraryError(f"ABI version mismatch: library {lib.pnr_version()}, binding 1")
+    if lib.pnr_version() != 2:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.pnr_version()}, binding 2")
     _lib = lib
     return lib
 

@@ -56,11 +56,12 @@ extern "C" int pnr_field_forward(const pnr_scene* scene, const pnr_points* pts, 
   if (rc) return rc;
   PNR_REQUIRE(params && out, PNR_ERR_ARG, "pnr_field_forward: null params/out");
   cudaStream_t st = (cudaStream_t)stream;
+  const int raw = (scene->flags & PNR_SCENE_RAW_OUTPUT) ? 1 : 0;
   if (precision == PNR_PREC_FP32) {
     PNR_REQUIRE(params->d_hidden == kHidden, PNR_ERR_UNSUPPORTED, "pnr_field_forward: d_hidden=%d", params->d_hidden);
-    return field_forward_fp32(scene, pts, params, out, workspace, workspace_bytes, num_freqs, freq_factor, 0, st);
+    return field_forward_fp32(scene, pts, params, out, workspace, workspace_bytes, num_freqs, freq_factor, raw, st);
   }
   if (precision == PNR_PREC_BF16)
-    return field_forward_umma(scene, pts, params, packed, out, workspace, workspace_bytes, num_freqs, freq_factor, 0, st);
+    return field_forward_umma(scene, pts, params, packed, out, workspace, workspace_bytes, num_freqs, freq_factor, raw, st);
   PNR_REQUIRE(false, PNR_ERR_ARG, "pnr_field_forward: unknown precision %d", precision);
 }

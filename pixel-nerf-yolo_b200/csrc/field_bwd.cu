@@ -399,6 +399,7 @@ static int check_train(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   if (rc) return rc;
   PNR_REQUIRE(mp, PNR_ERR_ARG, "%s: null params", who);
   PNR_REQUIRE(sc->feat_fp32, PNR_ERR_ARG, "%s: the training path reads fp32 channels-last feature maps", who);
+  PNR_REQUIRE(sc->flags == 0, PNR_ERR_UNSUPPORTED, "%s: the YOLO mode (scene flags %d) has no training path yet", who, sc->flags);
   PNR_REQUIRE(sc->C % 4 == 0, PNR_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 4", who, sc->C);
   PNR_REQUIRE(mp->d_latent == sc->C, PNR_ERR_ARG, "%s: d_latent=%d but maps have C=%d", who, mp->d_latent, sc->C);
   PNR_REQUIRE(mp->d_in == 6 * num_freqs + 6, PNR_ERR_ARG, "%s: d_in/num_freqs mismatch", who);

@@ -63,6 +63,8 @@ __device__ __forceinline__ Projection project_point(const pnr_scene& sc, int row
   // grid_sample(align_corners=True): ((g + 1) / 2) * (size - 1)
   o.ix = ((gx + 1.0f) * 0.5f) * (float)(sc.Wl - 1);
   o.iy = ((gy + 1.0f) * 0.5f) * (float)(sc.Hl - 1);
+  // YOLO mode: latent[z >= 0] = 0 (models.py:223,254-264) -- NaN coordinates fail every bounds test in make_taps
+  if ((sc.flags & PNR_SCENE_MASK_NONNEG_Z) && zc >= 0.0f) o.ix = o.iy = __int_as_float(0x7fc00000);
   return o;
 }
 

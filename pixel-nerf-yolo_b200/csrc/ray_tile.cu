@@ -306,6 +306,39 @@ __global__ void sample_depth_bwd_kernel(const float* __restrict__ z_sorted, cons
   if (lane == 0) d_depth[b] = acc;
 }
 
+
+// YoloRenderer.forward's per-ray reduction (src/render/yolo.py:96-114): raw field values (B, K, A*7) -> (B, A, 7) =
+// [max_k p, sum_k(v * p) / (sum_k p + 1e-5)] with p = sigmoid(value 0 of the anchor).  One warp per (ray, anchor).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+yolo_reduce_kernel(const float* __restrict__ out, float* __restrict__ res, long long n_pairs, int K, int A) {
+  const int lane = threadIdx.x & 31;
+  const long long pa = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (pa >= n_pairs) return;
+  const long long b = pa / A;
+  const int a = (int)(pa - b * A);
+  const float* o = out + (size_t)b * K * A * 7 + a * 7;
+  float sp = 0.f, mp = -1.0f, sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < K; k += 32) {
+    const float* v = o + (size_t)k * A * 7;
+    const float p = 1.0f / (1.0f + expf(-v[0]));
+    sp += p;
+    mp = fmaxf(mp, p);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sv[j] += v[1 + j] * p;
+  }
+  sp = warp_sum(sp);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mp = fmaxf(mp, __shfl_xor_sync(0xffffffffu, mp, d));
+#pragma unroll
+  for (int j = 0; j < 6; ++j) sv[j] = warp_sum(sv[j]);
+  if (lane == 0) {
+    float* r = res + pa * 7;
+    r[0] = mp;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r[1 + j] = __fdiv_rn(sv[j], __fadd_rn(sp, 1e-5f));
+  }
+}
+
 }  // namespace pnr
 
 using namespace pnr;
@@ -384,5 +417,17 @@ extern "C" int pnr_sample_fine_depth_backward(const float* z_sorted, const float
   sample_depth_bwd_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(z_sorted, d_z_sorted, depth, gauss, rays,
                                                                          d_depth, B, K, Kfd, depth_std);
   PNR_CHECK_LAUNCH("sample_depth_bwd_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_yolo_reduce(const float* out, float* result, int B, int K, int num_anchors, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(out && result, PNR_ERR_ARG, "pnr_yolo_reduce: null pointer");
+  PNR_REQUIRE(B >= 0 && K > 0 && num_anchors > 0, PNR_ERR_ARG, "pnr_yolo_reduce: bad shape");
+  if (B == 0) return PNR_OK;
+  const long long n = (long long)B * num_anchors;
+  yolo_reduce_kernel<<<(unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      out, result, n, K, num_anchors);
+  PNR_CHECK_LAUNCH("yolo_reduce_kernel");
   return PNR_OK;
 }

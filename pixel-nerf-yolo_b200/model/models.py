@@ -112,14 +112,17 @@ class PixelNeRFNet(torch.nn.Module):
         self.mlp_fine = make_mlp(conf["mlp_fine"], d_in, d_latent, allow_empty=True)
         self.register_buffer("poses", torch.empty(1, 3, 4), persistent=False)
         self.register_buffer("image_shape", torch.empty(2), persistent=False)
+        # YOLO head (models.py:75-81): raw per-anchor values, poses/focal used as given, latent masked where z >= 0
         self.yolo = conf.get_bool("mlp_coarse.yolo", False)
-        if self.yolo:
-            raise NotImplementedError("PixelNeRFNet (B200 path): the YOLO head (mlp_coarse.yolo) is the next row "
-                                      "after the NeRF path (SURVEY.md section 8f) and is not built yet")
         self.d_in = d_in
-        self.d_out = conf.get_int("mlp_coarse.d_out", 4)
-        if self.d_out != 4:
-            raise NotImplementedError("PixelNeRFNet (B200 path): d_out must be 4 (rgb + sigma)")
+        if not self.yolo:
+            self.d_out = conf.get_int("mlp_coarse.d_out", 4)
+            if self.d_out != 4:
+                raise NotImplementedError("PixelNeRFNet (B200 path): d_out must be 4 (rgb + sigma) outside YOLO mode")
+        else:
+            self.d_out = conf.get_int("mlp_coarse.d_out", 7) * conf.get_int("mlp_coarse.num_anchors_per_scale", 3)
+            if self.d_out > 32:
+                raise NotImplementedError("PixelNeRFNet (B200 path): YOLO head wider than 32 outputs is not built")
         self.d_latent = d_latent
         self.register_buffer("focal", torch.empty(1, 2), persistent=False)
         self.register_buffer("c", torch.empty(1, 2), persistent=False)
@@ -148,9 +151,12 @@ class PixelNeRFNet(torch.nn.Module):
 
     def set_cameras(self, poses, focal, image_wh, c=None):
         """The camera half of ``encode`` (models.py:116-148) without running the encoder trunk."""
-        rot = poses[:, :3, :3].transpose(1, 2)
-        trans = -torch.bmm(rot, poses[:, :3, 3:])
-        self.poses = torch.cat((rot, trans), dim=-1).float()
+        if not self.yolo:
+            rot = poses[:, :3, :3].transpose(1, 2)
+            trans = -torch.bmm(rot, poses[:, :3, 3:])
+            self.poses = torch.cat((rot, trans), dim=-1).float()
+        else:
+            self.poses = poses[:, :3, :4].float()            # models.py:119-120: already world -> camera
         self.image_shape[0] = image_wh[0]
         self.image_shape[1] = image_wh[1]
         if len(focal.shape) == 0:
@@ -160,7 +166,8 @@ class PixelNeRFNet(torch.nn.Module):
         else:
             focal = focal.clone()
         self.focal = focal.float().to(self.poses.device)
-        self.focal[..., 1] *= -1.0
+        if not self.yolo:
+            self.focal[..., 1] *= -1.0                       # models.py:136-137
         if c is None:
             c = (self.image_shape * 0.5).unsqueeze(0)
         elif len(c.shape) == 0:
@@ -192,7 +199,9 @@ class PixelNeRFNet(torch.nn.Module):
                 if t.shape[0] == n_views:
                     return t.contiguous()
                 raise AssertionError(f"focal/c has {t.shape[0]} rows for {SB} objects x {NS} views")
-            self._cam_cache = (self.poses.contiguous(), per_view(self.focal), per_view(self.c),
+            # the kernels compute uv = -xy / z * focal + c (models.py:220); YOLO mode is uv = +xy / z * focal + c (:222)
+            focal_k = -self.focal if self.yolo else self.focal
+            self._cam_cache = (self.poses.contiguous(), per_view(focal_k), per_view(self.c),
                                float(self.image_shape[0]), float(self.image_shape[1]),
                                float(self.encoder.latent_scaling[0]), float(self.encoder.latent_scaling[1]))
         poses, focal, center, iw, ih, lsx, lsy = cams if cams is not None else self._cam_cache
@@ -201,6 +210,7 @@ class PixelNeRFNet(torch.nn.Module):
         sc.feat, sc.poses, sc.focal, sc.center = feat.data_ptr(), poses.data_ptr(), focal.data_ptr(), center.data_ptr()
         sc.SB, sc.NS, sc.C, sc.Hl, sc.Wl = SB, NS, feat.shape[3], feat.shape[1], feat.shape[2]
         sc.feat_fp32 = int(fp32_maps)
+        sc.flags = (_lib.SCENE_MASK_NONNEG_Z | _lib.SCENE_RAW_OUTPUT) if self.yolo else 0
         sc.image_w, sc.image_h, sc.lat_scale_x, sc.lat_scale_y = iw, ih, lsx, lsy
         return sc, (poses, focal, center, iw, ih, lsx, lsy)
 
@@ -212,7 +222,7 @@ class PixelNeRFNet(torch.nn.Module):
         _lib.require_device(dev)
         lib = _lib.load()
         mlp = self._mlp(coarse)
-        out = torch.empty(SB, P, 4, device=dev, dtype=torch.float32)
+        out = torch.empty(SB, P, self.d_out, device=dev, dtype=torch.float32)
         if P == 0:
             return out
         launches = 0
@@ -267,6 +277,9 @@ class PixelNeRFNet(torch.nn.Module):
         """True when this call must record a backward pass (the reference just runs under autograd)."""
         if not (torch.is_grad_enabled() and self.training):      # inference callers use .eval() and/or no_grad()
             return False
+        if self.yolo:
+            raise NotImplementedError("PixelNeRFNet (B200 path): the YOLO head has no backward pass yet; run it under "
+                                      "torch.no_grad() / .eval()")
         if any(t is not None and t.requires_grad for t in tensors):
             return True
         if any(p.requires_grad for p in self._mlp(coarse).parameters()):
@@ -296,7 +309,7 @@ class PixelNeRFNet(torch.nn.Module):
         if self.precision == "bf16":
             pts = _lib.Points()
             pts.rays, pts.z, pts.mode, pts.P, pts.K = rays.data_ptr(), z.data_ptr(), 1, Bp * K, K
-            return self._run_field(pts, sb, Bp * K, coarse, (rays, z)).reshape(Bt, K, 4)
+            return self._run_field(pts, sb, Bp * K, coarse, (rays, z)).reshape(Bt, K, self.d_out)
         # fp32 check path: bound the workspace by chunking rays (results do not depend on the chunking)
         step = max(1, self.fp32_chunk_points // max(K * self.num_views_per_obj * sb, 1))
         outs = []
@@ -306,8 +319,8 @@ class PixelNeRFNet(torch.nn.Module):
             n = rc.shape[1]
             pts = _lib.Points()
             pts.rays, pts.z, pts.mode, pts.P, pts.K = rc.data_ptr(), zc.data_ptr(), 1, n * K, K
-            outs.append(self._run_field(pts, sb, n * K, coarse, (rc, zc)).reshape(sb, n, K, 4))
-        return torch.cat(outs, dim=1).reshape(Bt, K, 4)
+            outs.append(self._run_field(pts, sb, n * K, coarse, (rc, zc)).reshape(sb, n, K, self.d_out))
+        return torch.cat(outs, dim=1).reshape(Bt, K, self.d_out)
 
     # ------------------------------------------------------------------------------------------------
     def load_weights(self, args, opt_init=False, strict=True, device=None):

@@ -57,7 +57,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pnr_version() == 1
+    assert lib.pnr_version() == 2
     # struct layouts agree with the header (sizes computed by the C compiler)
     src = '#include "pixelnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu",sizeof(pnr_scene),sizeof(pnr_points),sizeof(pnr_mlp_params),sizeof(pnr_mlp_grads));}'
     exe = os.path.join(ROOT, "pixel-nerf-yolo_b200", "csrc", "build", "sizes")
@@ -90,7 +90,13 @@ def test_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
         SpatialEncoder("resnet34", pretrained=False, index_padding="border")
     with pytest.raises(NotImplementedError):
-        make_renderer(ConfigTree.from_dict({"renderer": {"type": "yolo"}}))
+        make_renderer(ConfigTree.from_dict({"renderer": {"type": "volsdf"}}))
+    from pixel_nerf_yolo_b200.render import YoloRenderer
+    y = make_renderer(ConfigTree.from_dict({"renderer": {"type": "yolo", "n_coarse": 128},
+                                            "model": {"mlp_coarse": {"num_anchors_per_scale": 3}}}))
+    assert isinstance(y, YoloRenderer) and (y.n_coarse, y.num_anchors_per_scale) == (128, 3)
+    with pytest.raises(RuntimeError):
+        y(torch.zeros(4, 8))                          # no network bound
 
 
 def test_model_api_and_state_dict_names():
