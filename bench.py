@@ -46,6 +46,16 @@ def peaks():
     return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the field kernel per launch (mean of the coarse and the fine launch
+    of this workload), copied from the committed `ncu --set full` capture; None if no capture is recorded."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["field_pair_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (recipe of B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -224,8 +234,8 @@ def run_ours(args):
             "gpu_launches": launches * args.steps * 2,   # device loop + e2e loop
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": None,
-                         "kernel": "field_umma_kernel<3> (fused gather + ResnetFC), 2 launches per step",
+                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": ncu_traffic(),
+                         "kernel": "pair::field_pair_kernel<3> (fused projection + gather + PE + ResnetFC, tcgen05 cta_group::2), 2 launches per step",
                          "peak_kind": f"{pk['source']} sustained bf16 (kernel timed inside a long step); burst {pk['bf16_burst']}",
                          "frac_of_burst": (achieved / pk["bf16_burst"]) if achieved else None,
                          "kernel_ms_per_step": field_total_ms / args.steps},

@@ -120,6 +120,16 @@ int pnr_pyramid_pack(const float* const* levels, const int32_t* level_C, const i
 int pnr_gen_rays(const float* poses, const long long* pix_inds, float* rays, long long n_out, int N, int H, int W,
                  float fx, float fy, float cx, float cy, float z_near, float z_far, void* stream);
 
+/* ---- output side ------------------------------------------------------------------------------------------- */
+/* eval/eval.py:283-290: rgb (B,3) -> rgb_u8 (B,3) = uint8(clamp(rgb,0,1)*255); depth (B) -> depth_norm (B) =
+ * (depth - z_near) / (z_far - z_near).  Either output may be NULL. */
+int pnr_image_output(const float* rgb, const float* depth, uint8_t* rgb_u8, float* depth_norm, long long B,
+                     float z_near, float z_far, void* stream);
+/* train/trainlib/PixelNerfTrainer.py:147-157 with src/model/loss.py:92-104 (MSELoss, or L1Loss when use_l1): adds
+ * mean((rgb - gt)^2) (or mean |rgb - gt|) over n values to *loss (caller zeroes it) and, if d_rgb is non-NULL, writes
+ * d loss / d rgb (n). */
+int pnr_rgb_loss(const float* rgb, const float* gt, float* loss, float* d_rgb, long long n, int use_l1, void* stream);
+
 /* ---- project + 4-tap gather + positional encoding, stand-alone ---------------------------------- */
 /* models.py:168-230 + encoder.py:79-108 + code.py:30-42.  For every (object, view, point) row
  * r = (s*NS + v)*P + p writes latent_out[r, 0:C] (bf16 if out_fp32=0 else fp32) and zfeat_out[r, 0:42]

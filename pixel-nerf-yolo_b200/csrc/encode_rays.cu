@@ -97,6 +97,46 @@ __global__ void gen_rays_kernel(const float* __restrict__ poses, const long long
   o[6] = z_near; o[7] = z_far;
 }
 
+
+// Output side.
+// eval/eval.py:283-290: depth -> (depth - z_near) / (z_far - z_near); rgb -> uint8(clamp(rgb, 0, 1) * 255).
+__global__ void image_output_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, uint8_t* __restrict__ rgb_u8,
+                                    float* __restrict__ depth_norm, long long B, float z_near, float z_far) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  if (rgb_u8) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = fminf(fmaxf(rgb[i * 3 + c], 0.0f), 1.0f);           // torch.clamp (NaN propagates -> 0 below)
+      rgb_u8[i * 3 + c] = (uint8_t)(int)__fmul_rn(v, 255.0f);             // numpy astype(uint8): truncation
+    }
+  }
+  if (depth_norm) depth_norm[i] = __fdiv_rn(__fsub_rn(depth[i], z_near), __fsub_rn(z_far, z_near));
+}
+
+// PixelNerfTrainer.py:147-157 + src/model/loss.py:92-104: mean squared (or absolute) error between rendered and ground
+// truth rgb, and its gradient, in one pass.  loss is accumulated with one atomic per block (double partial sums).
+__global__ void __launch_bounds__(256)
+rgb_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, float* __restrict__ loss,
+                float* __restrict__ d_rgb, long long n, int use_l1, float grad_scale) {
+  __shared__ double part[8];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = __fsub_rn(rgb[i], gt[i]);
+    acc += use_l1 ? (double)fabsf(d) : (double)d * (double)d;
+    if (d_rgb) d_rgb[i] = use_l1 ? (d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f)) : 2.0f * d * grad_scale;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    atomicAdd(loss, (float)(t / (double)n));
+  }
+}
+
 }  // namespace pnr
 
 using namespace pnr;
@@ -137,5 +177,29 @@ extern "C" int pnr_gen_rays(const float* poses, const long long* pix_inds, float
   gen_rays_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, pix_inds, rays, n_out, N, H, W, fx,
                                                                                     fy, cx, cy, z_near, z_far);
   PNR_CHECK_LAUNCH("gen_rays_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_image_output(const float* rgb, const float* depth, uint8_t* rgb_u8, float* depth_norm, long long B,
+                                float z_near, float z_far, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE((rgb_u8 == nullptr || rgb) && (depth_norm == nullptr || depth) && (rgb_u8 || depth_norm), PNR_ERR_ARG,
+              "pnr_image_output: null pointer");
+  PNR_REQUIRE(B >= 0, PNR_ERR_ARG, "pnr_image_output: bad shape");
+  if (B == 0) return PNR_OK;
+  image_output_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rgb, depth, rgb_u8, depth_norm, B, z_near, z_far);
+  PNR_CHECK_LAUNCH("image_output_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_rgb_loss(const float* rgb, const float* gt, float* loss, float* d_rgb, long long n, int use_l1,
+                            void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(rgb && gt && loss, PNR_ERR_ARG, "pnr_rgb_loss: null pointer");
+  PNR_REQUIRE(n > 0, PNR_ERR_ARG, "pnr_rgb_loss: empty input (torch's mean loss of nothing is NaN; refuse instead)");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rgb_loss_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rgb, gt, loss, d_rgb, n, use_l1, 1.0f / (float)n);
+  PNR_CHECK_LAUNCH("rgb_loss_kernel");
   return PNR_OK;
 }

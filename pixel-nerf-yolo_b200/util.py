@@ -48,3 +48,21 @@ def gen_rays(poses, width, height, focal, z_near, z_far, c=None, ndc=False, pix_
                                       float(z_near), float(z_far), _lib.stream_ptr(dev))
     _lib.check(rc, "pnr_gen_rays")
     return rays
+
+
+def image_output(rgb, depth, z_near, z_far):
+    """eval/eval.py:283-290 in one kernel: rgb (..., 3) -> uint8 (clamp to [0, 1], x255, truncate), depth (...) ->
+    (depth - z_near) / (z_far - z_near).  Returns (rgb_u8, depth_norm) on the device."""
+    _lib.require_cuda(rgb, "rgb")
+    _lib.require_device(rgb.device)
+    dev = rgb.device
+    r, d = rgb.contiguous().float(), depth.contiguous().float()
+    n = d.numel()
+    assert r.numel() == 3 * n, "rgb must hold 3 values per depth value"
+    out_u8 = torch.empty(r.shape, device=dev, dtype=torch.uint8)
+    out_d = torch.empty(d.shape, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pnr_image_output(r.data_ptr(), d.data_ptr(), out_u8.data_ptr(), out_d.data_ptr(), n, float(z_near),
+                                          float(z_far), _lib.stream_ptr(dev))
+    _lib.check(rc, "pnr_image_output")
+    return out_u8, out_d

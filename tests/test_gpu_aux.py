@@ -92,3 +92,34 @@ def test_encode_uses_fused_pyramid_and_render_agrees():
     # same fp32 value up to the interpolation's rounding, then one bf16 rounding: at most 1 bf16 ulp apart
     assert (diff <= 2.0 ** -7 * b.float().abs().clamp_min(1e-3)).all()
     assert (a == b).float().mean() > 0.99
+
+
+def test_image_output_matches_eval_script_arithmetic():
+    """eval/eval.py:283-290 restated with the same torch/numpy calls."""
+    from pixel_nerf_yolo_b200.util import image_output
+    g = torch.Generator().manual_seed(0)
+    rgb = torch.rand(5000, 3, generator=g) * 1.4 - 0.2            # some values outside [0, 1]
+    depth = 0.8 + torch.rand(5000, generator=g)
+    u8, dn = image_output(rgb.cuda(), depth.cuda(), 0.8, 1.8)
+    ref_u8 = (torch.clamp(rgb, 0.0, 1.0).numpy() * 255).astype(np.uint8)
+    ref_d = ((depth - 0.8) / (1.8 - 0.8)).numpy()
+    assert np.array_equal(u8.cpu().numpy(), ref_u8)
+    np.testing.assert_allclose(dn.cpu().numpy(), ref_d, atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("use_l1", [False, True])
+def test_rgb_loss_matches_torch_loss_and_grad(use_l1):
+    """src/model/loss.py:92-104: MSELoss / L1Loss (the reference's own criterion objects) forward and backward."""
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.model.loss import get_rgb_loss
+    g = torch.Generator().manual_seed(1)
+    rgb, gt = torch.rand(4, 128, 3, generator=g), torch.rand(4, 128, 3, generator=g)
+    a = rgb.clone().requires_grad_(True)
+    crit = torch.nn.L1Loss() if use_l1 else torch.nn.MSELoss()
+    ref = crit(a, gt)
+    (ref * 1.7).backward()
+    b = rgb.cuda().requires_grad_(True)
+    ours = get_rgb_loss(ConfigTree.from_dict({"use_l1": use_l1}))(b, gt.cuda())
+    (ours * 1.7).backward()
+    assert abs(ours.item() - ref.item()) < 1e-6
+    np.testing.assert_allclose(b.grad.cpu().numpy(), a.grad.numpy(), atol=1e-8, rtol=1e-6)
