@@ -146,7 +146,9 @@ struct Smem {
 enum {
   B_W_FULL = 0, B_W_EMPTY = B_W_FULL + kStages, B_IN_READY = B_W_EMPTY + kStages, B_IN_FREE,
   B_X_FULL, B_H_FULL = B_X_FULL + kMT,          // one per feature tile
-  B_RDY = B_H_FULL + kMT, B_X_FREE = B_RDY + 4, B_COUNT
+  B_RDY = B_H_FULL + kMT, B_X_FREE = B_RDY + 4,
+  B_LAND,                                       // non-leader CTA only: remote rows of chunk 2*i have landed (st.async bytes)
+  B_COUNT = B_LAND + kMT
 };
 static_assert(B_COUNT <= 30, "barrier parity bits live in one 32-bit word");
 static_assert(Smem::total <= 227 * 1024, "shared memory budget");
@@ -210,7 +212,8 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
 }
 
 template <int NC, bool REMOTE, bool ADD_BIAS>
-__device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* vals, float bias, int lane, int kq, int row0) {
+__device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* vals, float bias, int lane, int kq, int row0,
+                                                 uint32_t async_bar = 0) {   // != 0: remote rows go out as st.async counted on that barrier
   const int g = lane >> 3, i = lane & 7;
   const int k = kq + 8 * g;                                     // first of the 8 features this lane stores, within the chunk
   const uint32_t kb_off = (uint32_t)(k >> 6) * kOperandKB;
@@ -232,8 +235,10 @@ __device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* 
     const uint32_t o2 = __byte_perm(p[4], p[5], 0x7632), o3 = __byte_perm(p[6], p[7], 0x7632);
     const uint32_t addr_e = base + kb_off + swz_offset(row0 + c0 + i, k & 63);
     const uint32_t addr_o = base + kb_off + swz_offset(row0 + c0 + 8 + i, k & 63);
-    if (REMOTE) { st_cluster_v4(addr_e, e0, e1, e2, e3); st_cluster_v4(addr_o, o0, o1, o2, o3); }
-    else { st_shared_v4(addr_e, e0, e1, e2, e3); st_shared_v4(addr_o, o0, o1, o2, o3); }
+    if (REMOTE) {
+      if (async_bar) { st_async_v4(addr_e, e0, e1, e2, e3, async_bar); st_async_v4(addr_o, o0, o1, o2, o3, async_bar); }
+      else { st_cluster_v4(addr_e, e0, e1, e2, e3); st_cluster_v4(addr_o, o0, o1, o2, o3); }
+    } else { st_shared_v4(addr_e, e0, e1, e2, e3); st_shared_v4(addr_o, o0, o1, o2, o3); }
   }
 }
 
@@ -251,7 +256,13 @@ __device__ long long* g_prof_pair = nullptr;
 //                blocks [CL, n_blocks), lin_out, sigmoid/relu.
 // So every MMA of the kernel runs at N = 128, and the post-combine layers need 1/G of the weight passes and
 // epilogue hand-offs per point that a per-tile post phase would.
-template <int NS>
+//
+// Epilogue exchange, ASYNC = true: the half of every epilogue unit that belongs to the peer CTA goes out as st.async
+// (16 bytes per store, counted on an mbarrier of the DESTINATION CTA), so the epilogue warps no longer sit in
+// fence.proxy.async.shared::cluster waiting for their remote rows to be performed (14.5 % of all warp-stall samples of the
+// synchronous version).  Rows landing in the leader are counted directly on the chunk barrier the MMA warp waits on; rows
+// landing in the non-leader are counted on its B_LAND barrier, and its otherwise idle warp 1 relays that to the leader.
+template <int NS, bool ASYNC>
 __global__ void __launch_bounds__(kThreads, 1)
 field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant__ CUtensorMap wmap,
                   const float* __restrict__ bias_x, const float* __restrict__ bias_h,
@@ -281,7 +292,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     mbar_init(bar(B_IN_READY), 2 * kGatherWarps);
     mbar_init(bar(B_IN_FREE), 1);
     for (int i = 0; i < kMT; ++i) { mbar_init(bar(B_X_FULL + i), 1); mbar_init(bar(B_H_FULL + i), 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(bar(B_RDY + i), kEpiWarps);
+    // chunk kc is produced by CTA kc % 2; in ASYNC mode even chunks need one more arrival: the relay of the non-leader CTA
+    for (int i = 0; i < 4; ++i) mbar_init(bar(B_RDY + i), kEpiWarps + ((ASYNC && (i & 1) == 0) ? 1 : 0));
+    for (int i = 0; i < kMT; ++i) mbar_init(bar(B_LAND + i), kEpiWarps);
     mbar_init(bar(B_X_FREE), 2 * kEpiWarps);
     fence_barrier_init();
   }
@@ -352,6 +365,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
             const uint32_t id = wait_id - 1;
             mbar_wait_cluster(bar(id), (ph >> id) & 1u);
             ph ^= (1u << id);
+            if (ASYNC) fence_proxy_async();             // rows that landed in this CTA by st.async
             tc_fence_after();
             PPROF_ADD(id == B_IN_READY ? 2 : 4);
           }
@@ -396,6 +410,22 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
        }
       }
       if (prof && lane == 0) prof[0] += clock64() - t_role0;
+    } else if (ASYNC) {
+      // ===================== relay (non-leader CTA): remote rows of the even chunks have landed here -> tell the leader
+      const int n_pub = G * 2 * sch.CL + 2 * (sch.n_blocks - sch.CL) + 1;     // publishes of each chunk per super group
+      uint32_t par = 0;
+      for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
+        for (int i = 0; i < n_pub; ++i) {
+#pragma unroll
+          for (int mt = 0; mt < kMT; ++mt) {
+            mbar_wait_cluster(bar(B_LAND + mt), par);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(lbar(B_RDY + 2 * mt));
+          }
+          par ^= 1;
+        }
+      }
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue warps ===================================================================
@@ -417,13 +447,26 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     };
     const long long t_role0 = prof ? clock64() : 0;
     const uint32_t peer = crank ^ 1u;
+    constexpr uint32_t kRemoteBytes = (kNCol / 2) * 32 * 2;        // remote half of one warp's unit: 32 columns x 32 features bf16
+    // barrier (in the peer CTA) that counts this CTA's st.async rows of chunk kc = 2*mt + crank
+    auto land_bar = [&](int kc) -> uint32_t { return crank == 0 ? mapa_u32(bar(B_LAND + (kc >> 1)), 1) : lbar(B_RDY + kc); };
     auto publish = [&](int kc) {                   // operand rows of chunk kc written -> tell the leader's MMA warp
       const long long tp0 = (prof && prof_warp) ? clock64() : 0;
-      fence_proxy_async_cluster();                 // waits until this warp's local AND remote rows are performed
-      tc_fence_before();
-      __syncwarp();
-      // the fence already made the rows visible where the tensor cores read them: no cluster-scope release needed
-      if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_RDY + kc)); else mbar_arrive_cluster_relaxed(lbar(B_RDY + kc)); }
+      if (ASYNC) {
+        fence_proxy_async();                       // local rows only; the remote rows are counted where they land
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (crank == 0) { mbar_arrive(bar(B_RDY + kc)); mbar_arrive_expect_tx_cluster(land_bar(kc), kRemoteBytes); }
+          else mbar_arrive_expect_tx_cluster(land_bar(kc), kRemoteBytes);      // = the leader's chunk barrier
+        }
+      } else {
+        fence_proxy_async_cluster();               // waits until this warp's local AND remote rows are performed
+        tc_fence_before();
+        __syncwarp();
+        // the fence already made the rows visible where the tensor cores read them: no cluster-scope release needed
+        if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_RDY + kc)); else mbar_arrive_cluster_relaxed(lbar(B_RDY + kc)); }
+      }
       if (prof && prof_warp && lane == 0) prof[18] += clock64() - tp0;
     };
     // both halves of a unit: columns [hs*32, hs*32+32) of tile `peer` (remote rows) then of tile `crank` (local rows)
@@ -432,7 +475,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       const uint32_t rem = mapa_u32(loc, peer);
       uint32_t v[kNCol / 2];
       tmem_ld<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);
-      store_transposed<kNCol / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (kNCol / 2));
+      store_transposed<kNCol / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (kNCol / 2), ASYNC ? land_bar(kc) : 0u);
       tmem_ld<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), v);
       store_transposed<kNCol / 2, false, true>(loc, v, bias, lane, qd * 32, hs * (kNCol / 2));
     };
@@ -505,7 +548,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           for (int c = 0; c < kNCol / 2; ++c)
             v[c] = (hs * (kNCol / 2) + c < NLIVE) ? __float_as_uint(__ldcg(src + (size_t)c * kHidden)) : 0u;
           tmem_st<kNCol / 2>(tlane + mt * 128 + t * kNCol + hs * (kNCol / 2), v);
-          if (half == 0) store_transposed<kNCol / 2, true, false>(mapa_u32(loc, peer), v, 0.f, lane, qd * 32, hs * (kNCol / 2));
+          if (half == 0) store_transposed<kNCol / 2, true, false>(mapa_u32(loc, peer), v, 0.f, lane, qd * 32, hs * (kNCol / 2), ASYNC ? land_bar(kc) : 0u);
           else store_transposed<kNCol / 2, false, false>(loc, v, 0.f, lane, qd * 32, hs * (kNCol / 2));
         }
         publish(kc);
@@ -686,6 +729,12 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
 }  // namespace pair
 
 // ---- host side ---------------------------------------------------------------------------------------------
+// PNR_ASYNC=0 selects the synchronous epilogue exchange (st.shared::cluster + cluster-scope proxy fence); default 1.
+static bool pair_async() {
+  static int cached = -1;
+  if (cached < 0) { const char* e = getenv("PNR_ASYNC"); cached = (e && atoi(e) == 0) ? 0 : 1; }
+  return cached != 0;
+}
 // PNR_ORDER=0 selects the K-chunk-outer pair order (experiments); default 1.  Read once: pack and launch must agree.
 static int pair_order() {
   static int cached = -1;
@@ -755,6 +804,7 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int G = pair::kNCol / PP;                        // tile pairs per super group (see field_pair_kernel)
+  const bool async_x = pair_async();
   const int n_groups = ((n_tiles + 1) / 2 + G - 1) / G;  // super groups
   long long* prof_dev = nullptr;
   if (getenv("PNR_PROF")) {
@@ -764,7 +814,7 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   }
 #define PNR_LAUNCH_PAIR(NSV)                                                                                     \
   case NSV: {                                                                                                    \
-    auto kern = pair::field_pair_kernel<NSV>;                                                                    \
+    auto kern = async_x ? pair::field_pair_kernel<NSV, true> : pair::field_pair_kernel<NSV, false>;             \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::Smem::total); \
     PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
     cudaLaunchConfig_t cfg = {};                                                                                 \
@@ -776,6 +826,7 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
     cfg.gridDim = dim3(sms / 2 * 2);                                                                             \
     int max_pairs = sms / 2, mc = 0;                                                                             \
     if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) == cudaSuccess && mc > 0 && mc < max_pairs) max_pairs = mc; \
+    if (const char* mp_env = getenv("PNR_MAX_PAIRS")) { const int v = atoi(mp_env); if (v > 0 && v < max_pairs) max_pairs = v; } /* experiments */ \
     const int n_pairs = n_groups < max_pairs ? n_groups : max_pairs;                                             \
     cfg.gridDim = dim3(n_pairs * 2);                                                                             \
     e = cudaLaunchKernelEx(&cfg, kern, *sc, *q, tmap, bx, bh, bo, out, xbar, sch, num_freqs, freq_factor, tiles_per_obj, \

@@ -286,6 +286,19 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a,
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Asynchronous 16-byte store into a peer CTA's shared memory: the bytes are counted on an mbarrier of the DESTINATION CTA
+// (complete_tx), so the sender never waits for the write to be performed (no fence on its side).
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar)
+               : "memory");
+}
+// One arrival on a (possibly remote) mbarrier that also announces `bytes` of st.async / bulk traffic for the current phase.
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {   // one full warp in EACH CTA, same dst offset
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
