@@ -473,11 +473,12 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     auto convert_unit = [&](uint32_t tcol, int kc, float bias) {
       const uint32_t loc = sbase + Smem::ring + kc * kChunkBytes;
       const uint32_t rem = mapa_u32(loc, peer);
-      uint32_t v[kNCol / 2];
-      tmem_ld<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);
+      uint32_t v[kNCol / 2], u[kNCol / 2];
+      tmem_ld_nowait<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);     // both halves in flight at once
+      tmem_ld_nowait<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), u);
+      tmem_ld_wait();
       store_transposed<kNCol / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (kNCol / 2), ASYNC ? land_bar(kc) : 0u);
-      tmem_ld<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), v);
-      store_transposed<kNCol / 2, false, true>(loc, v, bias, lane, qd * 32, hs * (kNCol / 2));
+      store_transposed<kNCol / 2, false, true>(loc, u, bias, lane, qd * 32, hs * (kNCol / 2));
     };
     auto x_epilogue = [&](int e) {                 // relu(x + cumulative bias) -> bf16 K-chunks
       for (int mt = 0; mt < kMT; ++mt) {

@@ -218,6 +218,11 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r) {
   tmem_ld_wait();
 }
 template <int NCOLS>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t* r) {   // caller issues tmem_ld_wait() before using r
+#pragma unroll
+  for (int c = 0; c < NCOLS; c += 16) tmem_ld16(taddr + c, r + c);
+}
+template <int NCOLS>
 __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r) {
 #pragma unroll
   for (int c = 0; c < NCOLS; c += 16) tmem_st16(taddr + c, r + c);
