@@ -61,6 +61,12 @@ typedef struct pnr_scene {
 #define PNR_SCENE_MASK_NONNEG_Z 1
 /* pnr_field_forward returns the raw lin_out values instead of [sigmoid(rgb), relu(sigma)] (models.py:309-310). */
 #define PNR_SCENE_RAW_OUTPUT 2
+/* `feat` holds the lin_z PRE-PROJECTIONS of the encoder output (pnr_project_features): n_linz x d_hidden channels, slice b =
+ * latent . lin_z[b].weight^T.  Bilinear interpolation and lin_z are both linear, so lin_z[b](gather(latent)) ==
+ * gather(slice b) (+ bias); the kernel then accumulates the gathered slice with an identity weight instead of streaming a
+ * d_latent-wide lin_z.  For wide latents (1 792-channel YOLO backbone maps) this removes 3/4 of the gather traffic and 45 % of
+ * the weight stages.  Needs `packed` from pnr_mlp_pack_projected.  bf16 tcgen05 path only. */
+#define PNR_SCENE_PROJECTED 4
 
 /* Where the query points of a field evaluation come from. */
 typedef struct pnr_points {
@@ -164,6 +170,14 @@ size_t pnr_mlp_pack_bytes(const pnr_mlp_params* p);
 /* Build the packed blob (device, caller-allocated, 1024-byte aligned) from fp32 parameters.
  * A derived cache: rebuilt after load_state_dict / optimizer steps, never saved. */
 int pnr_mlp_pack(const pnr_mlp_params* p, void* packed, void* stream);
+
+/* Projected variant of the blob (see PNR_SCENE_PROJECTED): lin_z stages are identity matrices over d_hidden channels. */
+size_t pnr_mlp_pack_projected_bytes(const pnr_mlp_params* p);
+int pnr_mlp_pack_projected(const pnr_mlp_params* p, void* packed, void* stream);
+/* feat (n_pixels, d_latent) fp32 channels-last encoder output -> out (n_pixels, n_linz * d_hidden) bf16, slice b =
+ * feat . lin_z[b].weight^T (no bias; fp32 arithmetic, one rounding).  workspace: n_pixels * d_hidden floats. */
+int pnr_project_features(const pnr_mlp_params* p, const float* feat, long long n_pixels, void* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- field function: PixelNeRFNet.forward (src/model/models.py:153-318) -------------------------- */
 /* out (SB*P, 4) fp32 = [sigmoid(rgb), relu(sigma)].  precision PNR_PREC_FP32 uses `params` and a

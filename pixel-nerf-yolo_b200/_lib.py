@@ -19,6 +19,7 @@ PREC_FP32 = 0
 PREC_BF16 = 1
 SCENE_MASK_NONNEG_Z = 1
 SCENE_RAW_OUTPUT = 2
+SCENE_PROJECTED = 4
 
 # every symbol include/pixelnerf_b200.h declares
 EXPORTS = [
@@ -29,6 +30,7 @@ EXPORTS = [
     "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench",
     "pnr_field_tape_bytes", "pnr_field_forward_train", "pnr_field_backward_workspace_bytes", "pnr_field_backward",
     "pnr_composite_backward", "pnr_sample_fine_depth_backward", "pnr_pyramid_pack", "pnr_gen_rays", "pnr_yolo_reduce", "pnr_image_output", "pnr_rgb_loss",
+    "pnr_mlp_pack_projected_bytes", "pnr_mlp_pack_projected", "pnr_project_features",
 ]
 
 
@@ -117,6 +119,10 @@ def load() -> C.CDLL:
     lib.pnr_sample_fine_depth_backward.argtypes = [vp] * 6 + [i32, i32, i32, f32, vp]
     lib.pnr_pyramid_pack.argtypes = [C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      i32, i32, vp, i32, vp]
+    lib.pnr_mlp_pack_projected_bytes.argtypes = [C.POINTER(MlpParams)]
+    lib.pnr_mlp_pack_projected_bytes.restype = C.c_size_t
+    lib.pnr_mlp_pack_projected.argtypes = [C.POINTER(MlpParams), vp, vp]
+    lib.pnr_project_features.argtypes = [C.POINTER(MlpParams), vp, C.c_longlong, vp, vp, C.c_size_t, vp]
     lib.pnr_image_output.argtypes = [vp, vp, vp, vp, C.c_longlong, f32, f32, vp]
     lib.pnr_rgb_loss.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp]
     lib.pnr_yolo_reduce.argtypes = [vp, vp, i32, i32, i32, vp]

@@ -373,6 +373,16 @@ gather_encode_bwd_kernel(pnr_scene sc, pnr_points q, const float* __restrict__ d
   }
 }
 
+// fp32 (rows, H) -> bf16 slice of a wider channels-last map
+__global__ void store_bf16_slice_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int H,
+                                        int ld_dst, int c0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  const long long r = i / H;
+  const int c = (int)(i - r * H);
+  dst[r * ld_dst + c0 + c] = __float2bfloat16_rn(src[i]);
+}
+
 struct Tape {
   float *lat, *zf;
   float* X[9];      // rows x H: input of pre-combine block b (b < CL); X[CL] = output of the last pre-combine block
@@ -537,6 +547,33 @@ extern "C" int pnr_field_backward(const pnr_scene* sc, const pnr_points* q, cons
     gather_encode_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(*sc, *q, dlat, dzf, d_feat, d_xyz, d_z, num_freqs, freq_factor, rows);
     PNR_CHECK_LAUNCH("bwd::gather_encode_bwd_kernel");
     ++launches;
+  }
+  reset_launch_count();
+  count_launch(launches);
+  return PNR_OK;
+}
+
+extern "C" int pnr_project_features(const pnr_mlp_params* p, const float* feat, long long n_pixels, void* out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(p && feat && out && workspace, PNR_ERR_ARG, "pnr_project_features: null pointer");
+  PNR_REQUIRE(p->d_latent > 0 && p->d_hidden > 0 && p->combine_layer >= 1 && p->combine_layer <= 8, PNR_ERR_ARG,
+              "pnr_project_features: bad MLP dimensions");
+  PNR_REQUIRE(n_pixels >= 0 && n_pixels < (1LL << 31), PNR_ERR_ARG, "pnr_project_features: bad pixel count");
+  const int H = p->d_hidden, C = p->d_latent, n_linz = p->combine_layer < p->n_blocks ? p->combine_layer : p->n_blocks;
+  PNR_REQUIRE(workspace_bytes >= (size_t)n_pixels * H * sizeof(float), PNR_ERR_ARG, "pnr_project_features: workspace too small");
+  if (n_pixels == 0) return PNR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* tmp = (float*)workspace;
+  int launches = 0;
+  for (int b = 0; b < n_linz; ++b) {
+    PNR_REQUIRE(p->linz_w[b], PNR_ERR_ARG, "pnr_project_features: lin_z %d missing", b);
+    int rc = linear_fwd(feat, C, p->linz_w[b], nullptr, nullptr, tmp, n_pixels, H, C, false, st);
+    if (rc) return rc;
+    const long long n = n_pixels * H;
+    store_bf16_slice_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tmp, (__nv_bfloat16*)out, n_pixels, H, n_linz * H, b * H);
+    PNR_CHECK_LAUNCH("bwd::store_bf16_slice_kernel");
+    launches += 2;
   }
   reset_launch_count();
   count_launch(launches);

@@ -117,22 +117,22 @@ __host__ __device__ inline StageSrc decode_stage(const Sched& sc, int s) {
 }
 
 // CTA-pair kernel (mlp_umma_pair.cu)
-size_t pair_stream_bytes(const pnr_mlp_params* p);
-int pair_pack(const pnr_mlp_params* p, uint8_t* stream, cudaStream_t st);
+size_t pair_stream_bytes(const pnr_mlp_params* p, int proj);
+int pair_pack(const pnr_mlp_params* p, uint8_t* stream, int proj, cudaStream_t st);
 size_t pair_workspace_bytes();
 int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const uint8_t* stream,
                        const float* bx, const float* bh, const float* bo, float* out, void* ws, size_t ws_bytes,
-                       int num_freqs, float freq_factor, int raw, cudaStream_t st);
+                       int num_freqs, float freq_factor, int raw, int proj, cudaStream_t st);
 
 struct PackOffsets { size_t stages, bias_x, bias_h, bias_out, pair_stream, total; };
-static PackOffsets pack_offsets(const Sched& s, const pnr_mlp_params* p) {
+static PackOffsets pack_offsets(const Sched& s, const pnr_mlp_params* p, int proj = 0) {
   PackOffsets o;
   o.stages = kPackHeader;
   o.bias_x = o.stages + (size_t)sched_total(s) * kStageBytes;
   o.bias_h = o.bias_x + (size_t)(s.n_blocks + 1) * kHidden * sizeof(float);
   o.bias_out = o.bias_h + (size_t)s.n_blocks * kHidden * sizeof(float);
   o.pair_stream = (o.bias_out + 128 * sizeof(float) + 1023) & ~(size_t)1023;     // second copy of the weights, CTA-pair order
-  o.total = o.pair_stream + pair_stream_bytes(p);
+  o.total = o.pair_stream + pair_stream_bytes(p, proj);
   return o;
 }
 // PNR_PAIR=0 selects the single-CTA kernel, anything else (default) the CTA-pair kernel.
@@ -737,7 +737,15 @@ int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   PNR_REQUIRE(packed, PNR_ERR_ARG, "field_forward_umma: packed weights missing (call pnr_mlp_pack)");
   PNR_REQUIRE(((uintptr_t)packed & 1023) == 0, PNR_ERR_ARG, "field_forward_umma: packed blob must be 1024-byte aligned");
   PNR_REQUIRE(!sc->feat_fp32, PNR_ERR_ARG, "field_forward_umma: needs bf16 channels-last feature maps");
-  PNR_REQUIRE(sc->C == mp->d_latent, PNR_ERR_ARG, "field_forward_umma: feature maps have %d channels, the MLP expects %d", sc->C, mp->d_latent);
+  const int proj = (sc->flags & PNR_SCENE_PROJECTED) ? 1 : 0;
+  if (proj) {
+    PNR_REQUIRE(use_pair_kernel(), PNR_ERR_UNSUPPORTED, "field_forward_umma: projected feature maps need the CTA-pair kernel (PNR_PAIR=0 is set)");
+    PNR_REQUIRE(sc->C == sch.n_linz * kHidden, PNR_ERR_ARG, "field_forward_umma: projected maps must have n_linz x %d = %d channels (got %d)",
+                kHidden, sch.n_linz * kHidden, sc->C);
+    sch.KBz = kHidden / 64;              // blob from pnr_mlp_pack_projected: identity lin_z over 512 channels
+  } else {
+    PNR_REQUIRE(sc->C == mp->d_latent, PNR_ERR_ARG, "field_forward_umma: feature maps have %d channels, the MLP expects %d", sc->C, mp->d_latent);
+  }
   PNR_REQUIRE(mp->d_in == 6 * num_freqs + 6, PNR_ERR_ARG, "field_forward_umma: d_in/num_freqs mismatch");
   PNR_REQUIRE(sc->NS >= 1 && sc->NS <= 8 && sc->NS != 7, PNR_ERR_UNSUPPORTED, "field_forward_umma: NS=%d source views", sc->NS);
   if ((long long)sc->SB * q->P == 0) return PNR_OK;
@@ -757,14 +765,14 @@ int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
     cudaMemset(prof_dev, 0, (size_t)4096 * 32 * sizeof(long long));
     cudaMemcpyToSymbol(g_prof, &prof_dev, sizeof(prof_dev));
   }
-  const PackOffsets po = pack_offsets(sch, mp);
+  const PackOffsets po = pack_offsets(sch, mp, proj);
   const uint8_t* blob = (const uint8_t*)packed;
   const uint8_t* stages = blob + po.stages;
   const float* bx = (const float*)(blob + po.bias_x);
   const float* bh = (const float*)(blob + po.bias_h);
   const float* bo = (const float*)(blob + po.bias_out);
   if (use_pair_kernel())
-    return field_forward_pair(sc, q, mp, blob + po.pair_stream, bx, bh, bo, out, ws, ws_bytes, num_freqs, freq_factor, raw, st);
+    return field_forward_pair(sc, q, mp, blob + po.pair_stream, bx, bh, bo, out, ws, ws_bytes, num_freqs, freq_factor, raw, proj, st);
 #define PNR_LAUNCH_NS(NSV)                                                                                   \
   case NSV: {                                                                                                \
     auto kern = field_umma_kernel<NSV>;                                                                      \
@@ -818,29 +826,39 @@ int field_forward_umma(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
 
 using namespace pnr;
 
-extern "C" size_t pnr_mlp_pack_bytes(const pnr_mlp_params* p) {
+static size_t mlp_pack_bytes(const pnr_mlp_params* p, int proj) {
   Sched s;
   if (make_sched(p, &s, "pnr_mlp_pack_bytes")) return 0;
-  return pack_offsets(s, p).total;
+  if (proj) s.KBz = kHidden / 64;
+  return pack_offsets(s, p, proj).total;
 }
+extern "C" size_t pnr_mlp_pack_bytes(const pnr_mlp_params* p) { return mlp_pack_bytes(p, 0); }
+extern "C" size_t pnr_mlp_pack_projected_bytes(const pnr_mlp_params* p) { return mlp_pack_bytes(p, 1); }
 
-extern "C" int pnr_mlp_pack(const pnr_mlp_params* p, void* packed, void* stream) {
+static int mlp_pack(const pnr_mlp_params* p, void* packed, int proj, void* stream);
+extern "C" int pnr_mlp_pack(const pnr_mlp_params* p, void* packed, void* stream) { return mlp_pack(p, packed, 0, stream); }
+extern "C" int pnr_mlp_pack_projected(const pnr_mlp_params* p, void* packed, void* stream) { return mlp_pack(p, packed, 1, stream); }
+
+static int mlp_pack(const pnr_mlp_params* p, void* packed, int proj, void* stream) {
   reset_launch_count();
   Sched s;
   int rc = make_sched(p, &s, "pnr_mlp_pack");
   if (rc) return rc;
+  if (proj) s.KBz = kHidden / 64;
   PNR_REQUIRE(packed && ((uintptr_t)packed & 1023) == 0, PNR_ERR_ARG, "pnr_mlp_pack: packed must be non-null and 1024-byte aligned");
   PNR_REQUIRE(p->lin_in_w && p->lin_in_b && p->lin_out_w && p->lin_out_b, PNR_ERR_ARG, "pnr_mlp_pack: null lin_in/lin_out");
   for (int b = 0; b < p->n_blocks; ++b)
     PNR_REQUIRE(p->fc0_w[b] && p->fc0_b[b] && p->fc1_w[b] && p->fc1_b[b], PNR_ERR_ARG, "pnr_mlp_pack: null block %d", b);
   for (int b = 0; b < s.n_linz; ++b) PNR_REQUIRE(p->linz_w[b] && p->linz_b[b], PNR_ERR_ARG, "pnr_mlp_pack: null lin_z %d", b);
-  const PackOffsets po = pack_offsets(s, p);
+  const PackOffsets po = pack_offsets(s, p, proj);
   uint8_t* blob = (uint8_t*)packed;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = pair_pack(p, blob + po.pair_stream, st);
+  rc = pair_pack(p, blob + po.pair_stream, proj, st);
   if (rc) return rc;
-  pack_stages_kernel<<<sched_total(s), 256, 0, st>>>(*p, s, blob + po.stages);
-  PNR_CHECK_LAUNCH("pack_stages_kernel");
+  if (!proj) {      // the single-CTA kernel's stream (PNR_PAIR=0) has no projected mode; its slot in the blob stays unused
+    pack_stages_kernel<<<sched_total(s), 256, 0, st>>>(*p, s, blob + po.stages);
+    PNR_CHECK_LAUNCH("pack_stages_kernel");
+  }
   pack_bias_kernel<<<1, kHidden, 0, st>>>(*p, s, (float*)(blob + po.bias_x), (float*)(blob + po.bias_h),
                                           (float*)(blob + po.bias_out), (uint32_t*)blob);
   PNR_CHECK_LAUNCH("pack_bias_kernel");

@@ -45,7 +45,9 @@ constexpr int kTmemCols = 512;
 constexpr int kHCol = 256;
 constexpr int kMaxStages = 1024;
 
-struct Sched { int n_blocks, CL, n_linz, KBz, order; };   // order: (chunk, tile) pair order inside a layer, see fc_pair
+struct Sched { int n_blocks, CL, n_linz, KBz, order, proj; };   // order: (chunk, tile) pair order inside a layer, see fc_pair;
+// proj: the feature maps hold the lin_z pre-projections (512 channels per lin_z layer, PNR_SCENE_PROJECTED): every lin_z[b]
+// is an IDENTITY-weight accumulate of its own freshly gathered 512-channel slice (KBz = 8)
 enum { MAT_LIN_IN = 0, MAT_LINZ = 1, MAT_FC0 = 2, MAT_FC1 = 3, MAT_LIN_OUT = 4 };
 struct Seg { int kind, blk, t, len; };
 struct StageSrc { int mat, blk, row0, k0; };   // row0 = first row of the 256-row slab
@@ -125,11 +127,12 @@ __global__ void pack_stages_kernel(pnr_mlp_params mp, Sched sc, uint8_t* __restr
     case MAT_FC1: W = mp.fc1_w[src.blk]; rows = mp.d_hidden; cols = mp.d_hidden; break;
     default: W = mp.lin_out_w; rows = mp.d_out; cols = mp.d_hidden; break;
   }
+  const bool identity = sc.proj && src.mat == MAT_LINZ;
   uint8_t* dst = stages + ((size_t)s * 2 + half) * kStageBytes;
   for (int i = threadIdx.x; i < kStageRows * kBlockK; i += blockDim.x) {
     const int r = i / kBlockK, k = i % kBlockK;
     const int gr = src.row0 + half * 128 + r, gk = src.k0 + k;
-    const float v = (gr < rows && gk < cols) ? W[(size_t)gr * cols + gk] : 0.f;
+    const float v = identity ? (gr == gk ? 1.f : 0.f) : ((gr < rows && gk < cols) ? W[(size_t)gr * cols + gk] : 0.f);
     *reinterpret_cast<__nv_bfloat16*>(dst + swz_offset(r, k)) = __float2bfloat16_rn(v);
   }
 }
@@ -165,7 +168,7 @@ __device__ inline ProgEntry make_prog(const Sched& sc, int s, uint32_t sbase) {
       break;
     case MAT_LINZ: {
       const ZPos z = z_position(sc.KBz, g.t);
-      const bool streaming = z_passes(sc) > 1;
+      const bool streaming = z_passes(sc) > 1 || sc.proj;      // the latent tile is refilled for every pass / lin_z layer
       const bool pass_first = z.mt == 0 && z.kbi == 0, pass_last = z.mt == kMT - 1 && z.kbi == z.kp - 1;
       b_addr = sbase + Smem::lat + z.kbi * kOperandKB; dcol = z.mt * 128;
       if (streaming && pass_first && !(g.blk == 0 && z.pass == 0)) wait_id = B_IN_READY + 1;
@@ -593,7 +596,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     uint32_t par_free = 1;
     const long long t_role0 = prof ? clock64() : 0;
     const int n_pass = z_passes(sch);
-    const int fills = n_pass > 1 ? sch.n_linz * n_pass : 1;
+    const int fills = (n_pass > 1 || sch.proj) ? sch.n_linz * n_pass : 1;
     for (int it = 0;; ++it) {                        // tile pairs sg*G + g of super groups sg = pair_id, pair_id + n_pairs, ...
       const int sg = pair_id + (it / G) * n_pairs;
       if (sg >= n_sg) break;
@@ -640,7 +643,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       for (int fill = 0; fill < fills; ++fill) {
         const int pass = fill % n_pass;
         const int kp = sch.KBz - pass * 8 < 8 ? sch.KBz - pass * 8 : 8;
-        const int ch0 = pass * 512;
+        const int ch0 = sch.proj ? (fill / n_pass) * kHidden : pass * 512;   // projected maps: lin_z[b]'s own 512-channel slice
         {
           PPROF_T0();
           mbar_wait_cluster(bar(B_IN_FREE), par_free);
@@ -742,16 +745,19 @@ static int pair_order() {
   if (cached < 0) { const char* e = getenv("PNR_ORDER"); cached = (e && atoi(e) == 0) ? 0 : 1; }
   return cached;
 }
-size_t pair_stream_bytes(const pnr_mlp_params* p) {
-  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64, pair_order()};
+static pair::Sched pair_sched(const pnr_mlp_params* p, int proj) {
+  return pair::Sched{p->n_blocks, p->combine_layer, p->combine_layer, proj ? kHidden / 64 : p->d_latent / 64, pair_order(), proj};
+}
+size_t pair_stream_bytes(const pnr_mlp_params* p, int proj) {
+  pair::Sched s = pair_sched(p, proj);
   return (size_t)pair::sched_total(s) * 2 * kStageBytes;
 }
-int pair_stages(const pnr_mlp_params* p) {
-  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64, pair_order()};
+int pair_stages(const pnr_mlp_params* p, int proj) {
+  pair::Sched s = pair_sched(p, proj);
   return pair::sched_total(s);
 }
-int pair_pack(const pnr_mlp_params* p, uint8_t* stream, cudaStream_t st) {
-  pair::Sched s{p->n_blocks, p->combine_layer, p->combine_layer, p->d_latent / 64, pair_order()};
+int pair_pack(const pnr_mlp_params* p, uint8_t* stream, int proj, cudaStream_t st) {
+  pair::Sched s = pair_sched(p, proj);
   PNR_REQUIRE(pair::sched_total(s) <= pair::kMaxStages, PNR_ERR_UNSUPPORTED, "pair_pack: %d stages exceed the stage program", pair::sched_total(s));
   pair::pack_stages_kernel<<<pair::sched_total(s) * 2, 256, 0, st>>>(*p, s, stream);
   PNR_CHECK_LAUNCH("pair::pack_stages_kernel");
@@ -768,12 +774,12 @@ size_t pair_workspace_bytes() {
 
 int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const uint8_t* stream,
                        const float* bx, const float* bh, const float* bo, float* out, void* ws, size_t ws_bytes,
-                       int num_freqs, float freq_factor, int raw, cudaStream_t st) {
+                       int num_freqs, float freq_factor, int raw, int proj, cudaStream_t st) {
   PNR_REQUIRE(ws && ws_bytes >= pair_workspace_bytes() && ((uintptr_t)ws & 15) == 0, PNR_ERR_ARG,
               "field_forward_pair: workspace of pnr_field_workspace_bytes() = %zu bytes required (got %zu)",
               pair_workspace_bytes(), ws_bytes);
   float* xbar = (float*)ws;
-  pair::Sched sch{mp->n_blocks, mp->combine_layer, mp->combine_layer, mp->d_latent / 64, pair_order()};
+  pair::Sched sch = pair_sched(mp, proj);
   const int PP = pair::kNCol / sc->NS;
   const int tiles_per_obj = (q->P + PP - 1) / PP;
   const long long n_tiles_ll = (long long)tiles_per_obj * sc->SB;

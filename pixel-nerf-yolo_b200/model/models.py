@@ -130,6 +130,9 @@ class PixelNeRFNet(torch.nn.Module):
         self.num_views_per_obj = 1
         # "bf16": tcgen05 tensor-core path (production).  "fp32": SIMT fp32 check path.
         self.precision = "bf16"
+        # Latents wider than the hidden width (1 792-channel YOLO maps): gather lin_z PRE-PROJECTIONS of the maps instead of
+        # streaming the wide lin_z through the kernel (PNR_SCENE_PROJECTED).  None = automatic (d_latent > 512).
+        self.project_wide_latent = None
         self.fp32_chunk_points = 50000
         self._cam_cache = None
 
@@ -228,10 +231,18 @@ class PixelNeRFNet(torch.nn.Module):
         launches = 0
         with torch.cuda.device(dev):
             if self.precision == "bf16":
-                sc, keep2 = self._scene(fp32_maps=False)
+                proj = self.project_wide_latent
+                if proj is None:
+                    proj = mlp.d_latent > mlp.d_hidden
+                if proj:
+                    feat = mlp.project_features(self.encoder.packed_latent(fp32=True))
+                    sc, keep2 = self._scene_for(feat, fp32_maps=False)
+                    sc.flags |= _lib.SCENE_PROJECTED
+                else:
+                    sc, keep2 = self._scene(fp32_maps=False)
                 ws_bytes = lib.pnr_field_workspace_bytes(sc, pts, _lib.PREC_BF16)
                 ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)   # caching allocator: no cudaMalloc after the first call
-                rc = lib.pnr_field_forward(sc, pts, mlp.c_params(), mlp.packed().data_ptr(), out.data_ptr(),
+                rc = lib.pnr_field_forward(sc, pts, mlp.c_params(), mlp.packed(projected=proj).data_ptr(), out.data_ptr(),
                                            ws.data_ptr(), ws_bytes, _lib.PREC_BF16, self.code.num_freqs, self.code.freq_factor,
                                            _lib.stream_ptr(dev))
                 _lib.check(rc, "pnr_field_forward(bf16)")

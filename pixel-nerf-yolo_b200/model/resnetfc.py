@@ -98,9 +98,12 @@ class ResnetFC(nn.Module):
     def _param_key(self):
         return tuple((q.data_ptr(), q._version) for q in self.parameters())
 
-    def packed(self) -> torch.Tensor:
+    def packed(self, projected: bool = False) -> torch.Tensor:
         """bf16 tcgen05 weight stream + bias tables: a derived cache, rebuilt whenever a parameter changed
-        (optimizer step, load_state_dict, .to()); never part of the state_dict."""
+        (optimizer step, load_state_dict, .to()); never part of the state_dict.  ``projected``: the variant for
+        pre-projected feature maps (identity lin_z stages, ``PNR_SCENE_PROJECTED``)."""
+        if projected:
+            return self._packed_projected()
         key = self._param_key()
         if self._packed is None or self._packed_key != key:
             dev = self.lin_in.weight.device
@@ -118,6 +121,45 @@ class ResnetFC(nn.Module):
                 _lib.check(lib.pnr_mlp_pack(cp, blob.data_ptr(), _lib.stream_ptr(dev)), "pnr_mlp_pack")
             self._packed, self._packed_key = blob, key
         return self._packed
+
+    def _packed_projected(self) -> torch.Tensor:
+        key = self._param_key()
+        hit = getattr(self, "_packed_proj", None)
+        if hit is None or hit[0] != key:
+            dev = self.lin_in.weight.device
+            _lib.require_cuda(self.lin_in.weight, "ResnetFC parameters")
+            _lib.require_device(dev)
+            lib = _lib.load()
+            cp = self.c_params()
+            nbytes = lib.pnr_mlp_pack_projected_bytes(cp)
+            if nbytes == 0:
+                _lib.check(-3, "pnr_mlp_pack_projected_bytes")
+            buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+            off = (-buf.data_ptr()) % 1024
+            blob = buf[off:off + nbytes]
+            with torch.cuda.device(dev):
+                _lib.check(lib.pnr_mlp_pack_projected(cp, blob.data_ptr(), _lib.stream_ptr(dev)), "pnr_mlp_pack_projected")
+            self._packed_proj = (key, blob)
+        return self._packed_proj[1]
+
+    def project_features(self, feat_fp32_nhwc: torch.Tensor) -> torch.Tensor:
+        """(N, Hl, Wl, d_latent) fp32 channels-last encoder output -> (N, Hl, Wl, n_lin_z * d_hidden) bf16: slice b is the map
+        pushed through ``lin_z[b]`` (no bias).  Cached per (parameters, map): recomputed after an optimizer step or encode."""
+        key = (self._param_key(), feat_fp32_nhwc.data_ptr(), feat_fp32_nhwc._version, tuple(feat_fp32_nhwc.shape))
+        hit = getattr(self, "_projected", None)
+        if hit is None or hit[0] != key:
+            lib = _lib.load()
+            dev = feat_fp32_nhwc.device
+            n, h, w, c = feat_fp32_nhwc.shape
+            assert c == self.d_latent
+            out = torch.empty(n, h, w, len(self.lin_z) * self.d_hidden, device=dev, dtype=torch.bfloat16)
+            ws = torch.empty(n * h * w * self.d_hidden * 4, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.pnr_project_features(self.c_params(), feat_fp32_nhwc.data_ptr(), n * h * w, out.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _lib.stream_ptr(dev))
+            _lib.check(rc, "pnr_project_features")
+            self._projected = (key, out)
+        return self._projected[1]
 
     def forward(self, zx, combine_inner_dims=(1,), combine_index=None, dim_size=None):
         """Stand-alone operator, fp32 SIMT kernels: zx (..., d_latent + d_in) rows ordered

@@ -239,12 +239,16 @@ def test_field_other_latent_widths(lib, precision, tol, C, enc):
     P = 150
     xyz = (torch.rand(1, P, 3, generator=g) - 0.5) * 0.9
     dirs = torch.nn.functional.normalize(torch.randn(1, P, 3, generator=g), dim=-1)
-    with torch.no_grad():
-        out = net(xyz.cuda(), coarse=True, viewdirs=dirs.cuda()).cpu()
     ref = O.field_forward(H.oracle_scene(scene), synth.mlp_state(1, d_latent=C), xyz, dirs)
-    err_rgb = (out[..., :3] - ref[..., :3]).abs().max().item()
-    err_sig = ((out[..., 3] - ref[..., 3]).abs() / (1 + ref[..., 3].abs())).max().item()
-    assert err_rgb < tol and err_sig < tol, (err_rgb, err_sig)
+    # bf16: both ways of feeding a latent to lin_z -- streamed through the kernel in 512-channel passes, and (default for
+    # C > 512) the pre-projected maps with identity lin_z stages (PNR_SCENE_PROJECTED)
+    for project in ((False, True) if precision == "bf16" else (None,)):
+        net.project_wide_latent = project
+        with torch.no_grad():
+            out = net(xyz.cuda(), coarse=True, viewdirs=dirs.cuda()).cpu()
+        err_rgb = (out[..., :3] - ref[..., :3]).abs().max().item()
+        err_sig = ((out[..., 3] - ref[..., 3]).abs() / (1 + ref[..., 3].abs())).max().item()
+        assert err_rgb < tol and err_sig < tol, (project, err_rgb, err_sig)
 
 
 # ------------------------------------------------------------------------------------------------ render
