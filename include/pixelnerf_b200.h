@@ -67,6 +67,10 @@ typedef struct pnr_scene {
  * d_latent-wide lin_z.  For wide latents (1 792-channel YOLO backbone maps) this removes 3/4 of the gather traffic and 45 % of
  * the weight stages.  Needs `packed` from pnr_mlp_pack_projected.  bf16 tcgen05 path only. */
 #define PNR_SCENE_PROJECTED 4
+/* Training path only (pnr_field_forward_train / pnr_field_backward): run the GEMMs on the tensor cores with TF32 operands
+ * (10-bit mantissa) and fp32 accumulation instead of fp32 SIMT arithmetic: ~3x faster, gradients within ~5e-3 of autograd
+ * instead of ~1e-4. */
+#define PNR_SCENE_TRAIN_TF32 8
 
 /* Where the query points of a field evaluation come from. */
 typedef struct pnr_points {

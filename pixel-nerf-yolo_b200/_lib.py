@@ -20,6 +20,7 @@ PREC_BF16 = 1
 SCENE_MASK_NONNEG_Z = 1
 SCENE_RAW_OUTPUT = 2
 SCENE_PROJECTED = 4
+SCENE_TRAIN_TF32 = 8
 
 # every symbol include/pixelnerf_b200.h declares
 EXPORTS = [

@@ -48,29 +48,32 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
+  // 4 consecutive elements of one row: one 16-byte load when the run is inside the matrix and aligned
+  auto load4 = [](const float* base, long long row, long long ld, long long c, long long c_end, bool row_ok, float (&v)[4]) {
+    const float* p = base + row * ld + c;
+    if (row_ok && c + 4 <= c_end && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = (row_ok && c + e < c_end) ? p[e] : 0.f;
+    }
+  };
   for (long long k0 = kbeg; k0 < kend; k0 += BK) {
     float a[4], b[4];
     if (A_T) {          // i contiguous: thread -> (k = tid / 32, 4 consecutive i)
       const long long k = k0 + (tid >> 5);
-      const long long i = i0 + (tid & 31) * 4;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = (k < kend && i + e < g.I) ? g.A[k * g.lda + i + e] : 0.f;
+      load4(g.A, k, g.lda, i0 + (tid & 31) * 4, g.I, k < kend, a);
     } else {            // k contiguous: thread -> (i = tid / 2, 4 consecutive k)
       const long long i = i0 + (tid >> 1);
-      const long long k = k0 + (tid & 1) * 4;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = (i < g.I && k + e < kend) ? g.A[i * g.lda + k + e] : 0.f;
+      load4(g.A, i, g.lda, k0 + (tid & 1) * 4, kend, i < g.I, a);
     }
     if (!B_T) {         // j contiguous
       const long long k = k0 + (tid >> 5);
-      const int j = j0 + (tid & 31) * 4;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) b[e] = (k < kend && j + e < g.J) ? g.B[k * g.ldb + j + e] : 0.f;
+      load4(g.B, k, g.ldb, j0 + (tid & 31) * 4, g.J, k < kend, b);
     } else {            // k contiguous
-      const int j = j0 + (tid >> 1);
-      const long long k = k0 + (tid & 1) * 4;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) b[e] = (j < g.J && k + e < kend) ? g.B[(long long)j * g.ldb + k + e] : 0.f;
+      const long long j = j0 + (tid >> 1);
+      load4(g.B, j, g.ldb, k0 + (tid & 1) * 4, kend, j < g.J, b);
     }
     if (g.relu_a) {
 #pragma unroll
@@ -134,6 +137,137 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
   }
 }
 
+// Same contract on the tensor cores: TF32 operands (10-bit mantissa, round-to-nearest), fp32 accumulate, legacy
+// mma.sync.m16n8k8 -- the optional fast arithmetic of the training path (PNR_SCENE_TRAIN_TF32).  128x128x16 tiles, 8 warps
+// of 64x32; operands are rounded once when they are staged in shared memory (rows padded to 132 floats: conflict-free
+// fragment loads).
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+constexpr int TK = 16, TP = 132;
+template <bool A_T, bool B_T>
+__global__ void __launch_bounds__(256) sgemm_tf32_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[TK][TP];
+  __shared__ __align__(16) float Bs[TK][TP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+  const long long i0 = (long long)blockIdx.x * BM;
+  const int j0 = blockIdx.y * BN;
+  const long long kbeg = (long long)blockIdx.z * g.k_per_split;
+  const long long kend = kbeg + g.k_per_split < g.K ? kbeg + g.k_per_split : g.K;
+  float acc[4][4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  // 8 consecutive elements of one row: two 16-byte loads when the run is inside the matrix and aligned
+  auto load8 = [](const float* base, long long row, long long ld, long long c, long long c_end, bool row_ok, float (&v)[8]) {
+    const float* p = base + row * ld + c;
+    if (row_ok && c + 8 <= c_end && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(p)), y = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (row_ok && c + e < c_end) ? p[e] : 0.f;
+    }
+  };
+  for (long long k0 = kbeg; k0 < kend; k0 += TK) {
+    float a[8], b[8];
+    if (A_T) {          // i contiguous: thread -> (k = tid / 16, 8 consecutive i)
+      const long long k = k0 + (tid >> 4);
+      load8(g.A, k, g.lda, i0 + (tid & 15) * 8, g.I, k < kend, a);
+    } else {            // k contiguous: thread -> (i = tid / 2, 8 consecutive k)
+      const long long i = i0 + (tid >> 1);
+      load8(g.A, i, g.lda, k0 + (tid & 1) * 8, kend, i < g.I, a);
+    }
+    if (!B_T) {
+      const long long k = k0 + (tid >> 4);
+      load8(g.B, k, g.ldb, j0 + (tid & 15) * 8, g.J, k < kend, b);
+    } else {
+      const long long j = j0 + (tid >> 1);
+      load8(g.B, j, g.ldb, k0 + (tid & 1) * 8, kend, j < g.J, b);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (g.relu_a) a[e] = fmaxf(a[e], 0.f);
+      if (g.relu_b) b[e] = fmaxf(b[e], 0.f);
+      a[e] = to_tf32(a[e]);
+      b[e] = to_tf32(b[e]);
+    }
+    if (A_T) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) As[tid >> 4][(tid & 15) * 8 + e] = a[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) As[(tid & 1) * 8 + e][tid >> 1] = a[e];
+    }
+    if (!B_T) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) Bs[tid >> 4][(tid & 15) * 8 + e] = b[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) Bs[(tid & 1) * 8 + e][tid >> 1] = b[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < TK; ks += 8) {
+      uint32_t af[4][4], bf[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int m = wm + mi * 16 + gq;
+        af[mi][0] = __float_as_uint(As[ks + tq][m]);
+        af[mi][1] = __float_as_uint(As[ks + tq][m + 8]);
+        af[mi][2] = __float_as_uint(As[ks + tq + 4][m]);
+        af[mi][3] = __float_as_uint(As[ks + tq + 4][m + 8]);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int n = wn + ni * 8 + gq;
+        bf[ni][0] = __float_as_uint(Bs[ks + tq][n]);
+        bf[ni][1] = __float_as_uint(Bs[ks + tq + 4][n]);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[mi][ni][0]), "+f"(acc[mi][ni][1]), "+f"(acc[mi][ni][2]), "+f"(acc[mi][ni][3])
+                       : "r"(af[mi][0]), "r"(af[mi][1]), "r"(af[mi][2]), "r"(af[mi][3]), "r"(bf[ni][0]), "r"(bf[ni][1]));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const long long gi = i0 + wm + mi * 16 + gq + (c >> 1) * 8;
+        const int gj = j0 + wn + ni * 8 + tq * 2 + (c & 1);
+        if (gi >= g.I || gj >= g.J) continue;
+        const long long o = gi * g.ldc + gj;
+        float v = acc[mi][ni][c];
+        if (g.mask && !(g.mask[o] > 0.f)) v = 0.f;
+        if (g.mode == 0) {
+          if (g.bias) v += g.bias[gj];
+          if (g.add_src) v += g.add_src[o];
+          g.C[o] = v;
+        } else if (g.mode == 1) {
+          g.C[o] += v;
+        } else {
+          atomicAdd(g.C + o, v);
+        }
+      }
+}
+
+static thread_local int g_use_tf32 = 0;      // set per call from the scene flags (PNR_SCENE_TRAIN_TF32)
+
 static int launch_gemm(GemmArgs g, bool a_t, bool b_t, cudaStream_t st) {
   if (g.I == 0 || g.J == 0) return PNR_OK;
   int splits = 1;
@@ -145,10 +279,18 @@ static int launch_gemm(GemmArgs g, bool a_t, bool b_t, cudaStream_t st) {
     if (want > max_splits) want = max_splits;
     if (want < 1) want = 1;
     splits = (int)want;
-    g.k_per_split = ((g.K + splits - 1) / splits + BK - 1) / BK * BK;
+    g.k_per_split = ((g.K + splits - 1) / splits + TK - 1) / TK * TK;
     splits = (int)((g.K + g.k_per_split - 1) / g.k_per_split);
   }
   dim3 grid((unsigned)((g.I + BM - 1) / BM), (unsigned)((g.J + BN - 1) / BN), (unsigned)splits);
+  if (g_use_tf32) {
+    if (a_t && b_t) sgemm_tf32_kernel<true, true><<<grid, 256, 0, st>>>(g);
+    else if (a_t) sgemm_tf32_kernel<true, false><<<grid, 256, 0, st>>>(g);
+    else if (b_t) sgemm_tf32_kernel<false, true><<<grid, 256, 0, st>>>(g);
+    else sgemm_tf32_kernel<false, false><<<grid, 256, 0, st>>>(g);
+    PNR_CHECK_LAUNCH("bwd::sgemm_tf32_kernel");
+    return PNR_OK;
+  }
   if (a_t && b_t) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
   else if (a_t) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
   else if (b_t) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(g);
@@ -409,7 +551,8 @@ static int check_train(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   if (rc) return rc;
   PNR_REQUIRE(mp, PNR_ERR_ARG, "%s: null params", who);
   PNR_REQUIRE(sc->feat_fp32, PNR_ERR_ARG, "%s: the training path reads fp32 channels-last feature maps", who);
-  PNR_REQUIRE(sc->flags == 0, PNR_ERR_UNSUPPORTED, "%s: the YOLO mode (scene flags %d) has no training path yet", who, sc->flags);
+  PNR_REQUIRE((sc->flags & ~PNR_SCENE_TRAIN_TF32) == 0, PNR_ERR_UNSUPPORTED, "%s: the YOLO / projected modes (scene flags %d) have no training path yet", who, sc->flags);
+  g_use_tf32 = (sc->flags & PNR_SCENE_TRAIN_TF32) ? 1 : 0;
   PNR_REQUIRE(sc->C % 4 == 0, PNR_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 4", who, sc->C);
   PNR_REQUIRE(mp->d_latent == sc->C, PNR_ERR_ARG, "%s: d_latent=%d but maps have C=%d", who, mp->d_latent, sc->C);
   PNR_REQUIRE(mp->d_in == 6 * num_freqs + 6, PNR_ERR_ARG, "%s: d_in/num_freqs mismatch", who);
@@ -566,6 +709,7 @@ extern "C" int pnr_project_features(const pnr_mlp_params* p, const float* feat, 
   cudaStream_t st = (cudaStream_t)stream;
   float* tmp = (float*)workspace;
   int launches = 0;
+  g_use_tf32 = 0;
   for (int b = 0; b < n_linz; ++b) {
     PNR_REQUIRE(p->linz_w[b], PNR_ERR_ARG, "pnr_project_features: lin_z %d missing", b);
     int rc = linear_fwd(feat, C, p->linz_w[b], nullptr, nullptr, tmp, n_pixels, H, C, false, st);

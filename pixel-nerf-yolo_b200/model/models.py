@@ -133,6 +133,9 @@ class PixelNeRFNet(torch.nn.Module):
         # Latents wider than the hidden width (1 792-channel YOLO maps): gather lin_z PRE-PROJECTIONS of the maps instead of
         # streaming the wide lin_z through the kernel (PNR_SCENE_PROJECTED).  None = automatic (d_latent > 512).
         self.project_wide_latent = None
+        # arithmetic of the training path's GEMMs: "fp32" (SIMT, gradients equal autograd up to summation order) or "tf32"
+        # (mma.sync tensor cores, fp32 accumulate)
+        self.train_precision = "fp32"
         self.fp32_chunk_points = 50000
         self._cam_cache = None
 
@@ -214,6 +217,8 @@ class PixelNeRFNet(torch.nn.Module):
         sc.SB, sc.NS, sc.C, sc.Hl, sc.Wl = SB, NS, feat.shape[3], feat.shape[1], feat.shape[2]
         sc.feat_fp32 = int(fp32_maps)
         sc.flags = (_lib.SCENE_MASK_NONNEG_Z | _lib.SCENE_RAW_OUTPUT) if self.yolo else 0
+        if fp32_maps and self.train_precision == "tf32":
+            sc.flags |= _lib.SCENE_TRAIN_TF32            # read by the training entry points only
         sc.image_w, sc.image_h, sc.lat_scale_x, sc.lat_scale_y = iw, ih, lsx, lsy
         return sc, (poses, focal, center, iw, ih, lsx, lsy)
 

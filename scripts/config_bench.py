@@ -40,9 +40,10 @@ def flop_per_ray(ns, c, kc, kf, h=512, d_in=42, d_out=4):
     return per_pt * (kc + kc + kf)
 
 
-def config3():
+def config3(train_precision="fp32"):
     scene = H.make_scene_dict(num_objs=4, num_views=3, feat=64, size=128)
     net = H.build_net(scene, precision="bf16").train()
+    net.train_precision = train_precision
     lat = scene["latent"].to(dev).clone().requires_grad_(True)
     net.encoder.set_latent(lat)
     r = NeRFRenderer(64, 32, 16, white_bkgd=True).train().to(dev)
@@ -72,7 +73,7 @@ def config3():
             r(net, rays)
     t_inf = timed(infer)
     fl = flop_per_ray(3, 512, 64, 32) * 512
-    print(json.dumps({"config": 3, "workload": "train step: 4 objects x 128 rays, 3 views, 64+32 samples, fwd+bwd (fp32 SIMT training path)",
+    print(json.dumps({"config": 3, "workload": f"train step: 4 objects x 128 rays, 3 views, 64+32 samples, fwd+bwd ({train_precision} training path)",
                       "fwd_ms": round(t_f, 2), "fwd_bwd_ms": round(t_fb, 2), "rays_per_s_fwd_bwd": round(512 / (t_fb * 1e-3)),
                       "algorithmic_TFLOPs_fwd_bwd": round(3 * fl / (t_fb * 1e-3) / 1e12, 1),
                       "inference_same_rays_ms (bf16 tcgen05)": round(t_inf, 3)}))
@@ -113,3 +114,5 @@ def config5():
 which = [int(a) for a in sys.argv[1:]] or [3, 4, 5]
 for w in which:
     {3: config3, 4: config4, 5: config5}[w]()
+    if w == 3:
+        config3("tf32")

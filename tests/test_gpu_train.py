@@ -175,3 +175,29 @@ def test_train_step_config3_full_size(lib):
         close(gf_all[name], gf_a[name] + gf_b[name], f"fine d {name} additivity")
     close(lat_all, torch.cat((lat_a, lat_b)), "d latent per object")
     assert gc_all["lin_in.weight"].abs().max() > 0 and gf_all["lin_out.weight"].abs().max() > 0
+
+
+def test_train_step_tf32_tensor_core_arithmetic(lib):
+    """The training path's optional TF32 tensor-core GEMMs (net.train_precision = "tf32", PNR_SCENE_TRAIN_TF32): same step as
+    above, gradients within 2e-2 of each tensor's max (TF32 keeps 10 mantissa bits; 2e-2 is SURVEY.md 8c(4)'s bound for
+    reduced-precision gradients; measured 1.4e-2 on the depth-path gradient of the coarse lin_z, ~2e-3 elsewhere)."""
+    num_objs, nrays = 2, 24
+    scene = H.make_scene_dict(num_objs=num_objs, num_views=3, feat=16)
+    rays = H.rays_subset(num_objs, nrays, seed=3)
+    noise = H.make_noise(num_objs * nrays, seed=4)
+    gt = torch.rand(num_objs, nrays, 3, generator=torch.Generator().manual_seed(5))
+    loss_o, res_o, g_o = H.oracle_train_step(scene, rays, noise, gt)
+    net, lat = _train_net(scene)
+    net.train_precision = "tf32"
+    r = _renderer().train()
+    r.noise_override = {k: v.cuda() for k, v in noise.items()}
+    res = r(net, rays.cuda())
+    mse = torch.nn.functional.mse_loss
+    loss = mse(res.coarse.rgb, gt.cuda()) + mse(res.fine.rgb, gt.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_o.item()) <= 2e-3 * abs(loss_o.item())
+    np.testing.assert_allclose(res.fine.rgb.detach().cpu().numpy(), res_o["fine"]["rgb"].detach().numpy(), atol=3e-3, rtol=0)
+    for lvl, mlp in (("coarse", net.mlp_coarse), ("fine", net.mlp_fine)):
+        for name, gr in _named_grads(mlp).items():
+            close(gr, g_o[lvl][name], f"tf32 {lvl} d {name}", 2e-2)
+    close(lat.grad, g_o["latent"], "tf32 d latent", 2e-2)
