@@ -63,13 +63,26 @@ __host__ __device__ inline int sched_pre(const Sched& s) { return kMT + s.n_linz
 // Order of the (K-chunk kc, feature tile mt) pairs inside a 512x512 layer.  Chunks 0,1 come from the previous
 // layer's tile 0 and arrive first, so both output tiles consume them first; then tile 0 is finished (its
 // completion is signalled on its own barrier, so its epilogue overlaps the last two pairs), then tile 1.
-__host__ __device__ inline void fc_pair(int order, int t, int& kc, int& mt, int& kk) {
+// order 2 (default) additionally starts with the ODD chunk of each pair of chunks: odd chunks are produced by the non-leader
+// CTA and their remote rows land in the leader, on the very barrier the MMA warp waits on, while even chunks need the relay
+// hop from the non-leader (asynchronous exchange) -- that hop then overlaps the MMAs of the odd chunk.
+// first / last: this is the first / last (k-block of the) pair that touches output tile mt.
+__host__ __device__ inline void fc_pair(int order, int t, int& kc, int& mt, int& kk, bool& first, bool& last) {
   const int pr = t >> 1;                       // 0..7
   kk = t & 1;
-  if (order == 0) { kc = pr >> 1; mt = pr & 1; return; }        // K-chunk outer: (c0,t0)(c0,t1)(c1,t0)...
-  kc = (pr < 4) ? (pr & 1) : (2 + (pr & 1));                    // (c0,t0)(c1,t0)(c0,t1)(c1,t1)(c2,t0)(c3,t0)(c2,t1)(c3,t1)
+  if (order == 0) {                            // K-chunk outer: (c0,t0)(c0,t1)(c1,t0)...
+    kc = pr >> 1; mt = pr & 1;
+    first = pr < 2 && kk == 0; last = pr >= 6 && kk == 1;
+    return;
+  }
+  kc = (pr < 4) ? (pr & 1) : (2 + (pr & 1));   // (c0,t0)(c1,t0)(c0,t1)(c1,t1)(c2,t0)(c3,t0)(c2,t1)(c3,t1)
+  if (order == 2) kc ^= 1;                     // (c1,t0)(c0,t0)(c1,t1)(c0,t1)(c3,t0)(c2,t0)(c3,t1)(c2,t1)
   mt = (pr >> 1) & 1;
+  first = (pr == 0 || pr == 2) && kk == 0;
+  last = (pr == 5 || pr == 7) && kk == 1;
 }
+// chunk order of lin_out (one output tile): 0,1,2,3 or, for order 2, 1,0,3,2
+__host__ __device__ inline int out_chunk(int order, int t) { return order == 2 ? ((t >> 1) ^ 1) : (t >> 1); }
 __host__ __device__ inline Seg walk_stage(const Sched& sc, int s) {
   Seg g;
   const int s1 = kMT * sc.KBz;
@@ -109,8 +122,8 @@ __host__ __device__ inline StageSrc decode_stage(const Sched& sc, int s) {
     case MAT_LIN_IN: r.row0 = g.t * 256; r.k0 = 0; break;
     case MAT_LINZ: { const ZPos z = z_position(sc.KBz, g.t); r.row0 = z.mt * 256; r.k0 = (z.pass * 8 + z.kbi) * 64; } break;
     case MAT_FC0:
-    case MAT_FC1: { int kc, mt, kk; fc_pair(sc.order, g.t, kc, mt, kk); r.row0 = mt * 256; r.k0 = kc * 128 + kk * 64; } break;
-    default: r.row0 = 0; r.k0 = g.t * 64; break;
+    case MAT_FC1: { int kc, mt, kk; bool f, l; fc_pair(sc.order, g.t, kc, mt, kk, f, l); r.row0 = mt * 256; r.k0 = kc * 128 + kk * 64; } break;
+    default: r.row0 = 0; r.k0 = out_chunk(sc.order, g.t) * 128 + (g.t & 1) * 64; break;
   }
   return r;
 }
@@ -178,15 +191,16 @@ __device__ inline ProgEntry make_prog(const Sched& sc, int s, uint32_t sbase) {
     case MAT_FC0:
     case MAT_FC1: {
       int kc, mt, kk;
-      fc_pair(sc.order, g.t, kc, mt, kk);
+      bool first_of_tile, last_of_tile;
+      fc_pair(sc.order, g.t, kc, mt, kk, first_of_tile, last_of_tile);
       const bool fc0 = g.kind == MAT_FC0;
       b_addr = sbase + Smem::ring + (kc * 2 + kk) * kOperandKB; dcol = (fc0 ? kHCol : 0) + mt * 128;
-      if (fc0) acc = (kc > 0 || kk > 0);
+      if (fc0) acc = first_of_tile ? 0 : 1;                      // fc_1 always accumulates into x
       if (mt == 0 && kk == 0) wait_id = B_RDY + kc + 1;          // first use of chunk kc (tile 0 precedes tile 1 for every chunk)
-      if (kc == 3 && kk == 1) c2 = (fc0 ? B_H_FULL : B_X_FULL) + mt + 1;   // tile mt complete
+      if (last_of_tile) c2 = (fc0 ? B_H_FULL : B_X_FULL) + mt + 1;   // tile mt complete
     } break;
     default: {
-      const int kc = g.t / 2, kk = g.t % 2;
+      const int kc = out_chunk(sc.order, g.t), kk = g.t % 2;
       b_addr = sbase + Smem::ring + (kc * 2 + kk) * kOperandKB; dcol = kHCol; acc = g.t > 0;
       if (kk == 0) wait_id = B_RDY + kc + 1;
       if (last) c2 = B_H_FULL + 1;
@@ -739,10 +753,11 @@ static bool pair_async() {
   if (cached < 0) { const char* e = getenv("PNR_ASYNC"); cached = (e && atoi(e) == 0) ? 0 : 1; }
   return cached != 0;
 }
-// PNR_ORDER=0 selects the K-chunk-outer pair order (experiments); default 1.  Read once: pack and launch must agree.
+// PNR_ORDER=0 / 1 select the K-chunk-outer / tile-0-first pair orders (experiments); default 2 (see fc_pair).  Read once: pack
+// and launch must agree.
 static int pair_order() {
   static int cached = -1;
-  if (cached < 0) { const char* e = getenv("PNR_ORDER"); cached = (e && atoi(e) == 0) ? 0 : 1; }
+  if (cached < 0) { const char* e = getenv("PNR_ORDER"); cached = e ? atoi(e) : 2; if (cached < 0 || cached > 2) cached = 2; }
   return cached;
 }
 static pair::Sched pair_sched(const pnr_mlp_params* p, int proj) {
