@@ -34,7 +34,10 @@ namespace pair {
 constexpr int kNCol = 64;                    // columns per CTA tile
 constexpr int kMT = 2;                       // 256-feature tiles per 512-wide layer
 constexpr int kKBlocksH = kHidden / kBlockK; // 8
-constexpr int kStages = 5;
+#ifndef PNR_STAGES
+#define PNR_STAGES 5
+#endif
+constexpr int kStages = PNR_STAGES;   // weight ring depth (16 KiB each); -DPNR_STAGES=n builds an experiment
 constexpr int kThreads = 512;
 constexpr int kProducers = 3;                // warps 0,12,13
 constexpr int kGatherWarps = 4;              // warps 2,3,14,15
@@ -331,7 +334,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
   cluster_sync_all();                    // both CTAs' barriers initialised and TMEM allocated before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
+#ifdef PNR_DIAG_N   // timing diagnostic only (wrong results): same instruction stream, less tensor work per MMA
+  const uint32_t idesc = instr_desc_bf16_2sm(PNR_DIAG_N);
+#else
   const uint32_t idesc = instr_desc_bf16_2sm(2 * kNCol);
+#endif
 
   if (warp == 0 || warp == 12 || warp == 13) {
     // ===================== weight producers: warp p streams global stages g = p (mod kProducers); each CTA loads its
@@ -356,76 +363,66 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     }
   } else if (warp == 1) {
     if (crank == 0) {
-      // ===================== MMA issuer (leader CTA only): flat loop over the per-tile stage program ============
-      uint32_t slot = 0, wpar = 0, ready = 0, ph = 0;
+      // ===================== MMA issuer (leader CTA only): ONE thread walks the per-tile stage program ==========
+      // Measured (MMA N = 128 / 64 / 32 give the same step time): the tensor pipe is not what this kernel waits for, the
+      // issuing warp's own instruction stream is.  So the whole role is a single elected thread in a tight per-stage loop --
+      // no ballot probe of the ring, no per-batch elect / __syncwarp: it polls the barriers itself (try_wait), issues the four
+      // MMAs of the stage (~45 cycles) and its commits (~70 cycles), and prefetches the next program entry meanwhile.
       const long long t_role0 = prof ? clock64() : 0;
-      const uint64_t wdesc0 = smem_desc(sbase + Smem::w);
-      const uint64_t bdesc_hi = smem_desc(0);
-      constexpr uint64_t kStageStep = kStageBytes >> 4;
-      const uint2* prog = reinterpret_cast<const uint2*>(smem + Smem::prog);
-      for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
-       for (int seg = 0; seg <= G; ++seg) {              // G pre-combine passes, then the post-combine pass
-        if (seg > 0 && seg < G) {
-          // the view-mean epilogue of the previous tile must have read x out of TMEM before lin_in overwrites it
-          PPROF_T0();
-          mbar_wait_cluster(bar(B_X_FREE), (ph >> B_X_FREE) & 1u);
-          ph ^= (1u << B_X_FREE);
-          tc_fence_after();
-          PPROF_ADD(5);
-        }
-        const int st_end = seg < G ? s_pre : n_stages;
-        for (int st = seg < G ? 0 : s_pre; st < st_end;) {
-          const uint2 cur = prog[st];
-          const uint32_t wait_id = cur.x >> 25;
-          if (wait_id) {
-            PPROF_T0();
-            const uint32_t id = wait_id - 1;
-            mbar_wait_cluster(bar(id), (ph >> id) & 1u);
-            ph ^= (1u << id);
-            if (ASYNC) fence_proxy_async();             // rows that landed in this CTA by st.async
-            tc_fence_after();
-            PPROF_ADD(id == B_IN_READY ? 2 : 4);
-          }
-          if (ready == 0) {
-            PPROF_T0();
-            uint32_t my = slot + lane, mypar = wpar;
-            if (my >= kStages) { my -= kStages; mypar ^= 1; }
-            const bool ok = lane < kStages ? mbar_test_wait(bar(B_W_FULL + my), mypar) : false;
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            ready = __ffs(~m) - 1;
-            if (ready == 0) { mbar_wait(bar(B_W_FULL + slot), wpar); ready = 1; }
-            tc_fence_after();
-            PPROF_ADD(1);
-          }
-          const uint32_t run = (cur.y >> 10) & 15u;
-          const uint32_t batch = ready < run ? ready : run;
-          const long long t_issue0 = prof ? clock64() : 0;
-          if (elect_one()) {
-            uint2 en = cur;
-            uint32_t sl = slot;
-            for (uint32_t r = 0; r < batch; ++r) {
-              const uint2 ecur = en;
-              if (r + 1 < batch) en = prog[st + r + 1];
-              const uint64_t b_desc = bdesc_hi | (uint64_t)(ecur.x & 0x3FFFu);
-              const uint32_t d_col = (ecur.x >> 14) & 0x1FFu;
-              mma_kblock_desc_2sm(tmem_base + d_col, wdesc0 + sl * kStageStep, b_desc, idesc, (ecur.x >> 23) & 1u);
-              mma_commit_2sm(bar(B_W_EMPTY + sl), 3);
-              const uint32_t c1 = ecur.y & 31u, c2 = (ecur.y >> 5) & 31u, c3 = (ecur.y >> 14) & 31u;
+      if (elect_one()) {
+        uint32_t slot = 0, wpar = 0, ph = 0;
+        const uint64_t wdesc0 = smem_desc(sbase + Smem::w);
+        const uint64_t bdesc_hi = smem_desc(0);
+        constexpr uint64_t kStageStep = kStageBytes >> 4;
+        const uint2* prog = reinterpret_cast<const uint2*>(smem + Smem::prog);
+#define MPROF_T0() const long long t0__ = prof ? clock64() : 0
+#define MPROF_ADD(slot_) do { if (prof) prof[slot_] += clock64() - t0__; } while (0)
+        for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
+          for (int seg = 0; seg <= G; ++seg) {              // G pre-combine passes, then the post-combine pass
+            if (seg > 0 && seg < G) {
+              // the view-mean epilogue of the previous tile must have read x out of TMEM before lin_in overwrites it
+              MPROF_T0();
+              mbar_wait_cluster(bar(B_X_FREE), (ph >> B_X_FREE) & 1u);
+              ph ^= (1u << B_X_FREE);
+              tc_fence_after();
+              MPROF_ADD(5);
+            }
+            const int st_beg = seg < G ? 0 : s_pre, st_end = seg < G ? s_pre : n_stages;
+            uint2 cur = prog[st_beg];
+            for (int st = st_beg; st < st_end; ++st) {
+              const uint2 nxt = prog[st + 1 < st_end ? st + 1 : st];     // in flight while this stage is issued
+              const uint32_t wait_id = cur.x >> 25;
+              if (wait_id) {
+                MPROF_T0();
+                const uint32_t id = wait_id - 1;
+                mbar_wait_cluster(bar(id), (ph >> id) & 1u);
+                ph ^= (1u << id);
+                if (ASYNC) fence_proxy_async();             // rows that landed in this CTA by st.async
+                MPROF_ADD(id == B_IN_READY ? 2 : 4);
+              }
+              {
+                MPROF_T0();
+                mbar_wait(bar(B_W_FULL + slot), wpar);
+                MPROF_ADD(1);
+              }
+              tc_fence_after();
+              const uint64_t b_desc = bdesc_hi | (uint64_t)(cur.x & 0x3FFFu);
+              const uint32_t d_col = (cur.x >> 14) & 0x1FFu;
+              mma_kblock_desc_2sm(tmem_base + d_col, wdesc0 + slot * kStageStep, b_desc, idesc, (cur.x >> 23) & 1u);
+              mma_commit_2sm(bar(B_W_EMPTY + slot), 3);
+              const uint32_t c1 = cur.y & 31u, c2 = (cur.y >> 5) & 31u, c3 = (cur.y >> 14) & 31u;
               if (c1) mma_commit_2sm(bar(c1 - 1), 3);
               if (c2) mma_commit_2sm(bar(c2 - 1), 3);
               if (c3) mma_commit_2sm(bar(c3 - 1), 3);
-              sl = sl + 1 == kStages ? 0 : sl + 1;
+              if (++slot == kStages) { slot = 0; wpar ^= 1; }
+              cur = nxt;
             }
           }
-          __syncwarp();
-          if (prof && lane == 0) prof[6] += clock64() - t_issue0;
-          ready -= batch;
-          st += batch;
-          slot += batch;
-          if (slot >= kStages) { slot -= kStages; wpar ^= 1; }
         }
-       }
+#undef MPROF_T0
+#undef MPROF_ADD
       }
+      __syncwarp();
       if (prof && lane == 0) prof[0] += clock64() - t_role0;
     } else if (ASYNC) {
       // ===================== relay (non-leader CTA): remote rows of the even chunks have landed here -> tell the leader
@@ -865,7 +862,7 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
     cudaStreamSynchronize(st);
     std::vector<long long> h((size_t)4096 * 32);
     cudaMemcpy(h.data(), prof_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    const char* names[32] = {"mma_total", "mma_wait_weights", "mma_wait_gather", 0, "mma_wait_chunk", 0, "mma_issue_block", 0,
+    const char* names[32] = {"mma_total", "mma_wait_weights", "mma_wait_gather", 0, "mma_wait_chunk", "mma_wait_x_free", 0, 0,
                              "epi_total", "epi_wait_x_full", "epi_wait_h_full", 0, 0, 0, "epi_convert_x(x10 units)", 0,
                              "gather_total", "gather_wait_in_free", "epi_publish(x22)"};
     int ctas = 0, leaders = 0; double sum[32] = {0};
