@@ -344,23 +344,27 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     // ===================== weight producers: warp p streams global stages g = p (mod kProducers); each CTA loads its
     // 128-row half of every 256-row slab, both halves complete on the LEADER's W_FULL barrier
     const int pid = warp == 0 ? 0 : warp - 11;
-    uint32_t slot = pid, par = 1;
-    int carry = pid;                                    // first stage of this producer inside the current super group
-    for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
-      int fi = carry;
-      for (; fi < n_flat; fi += kProducers) {
-        const int st = fi < G * s_pre ? fi % s_pre : fi - (G - 1) * s_pre;   // G passes over the pre stages, one over the post stages
-        mbar_wait_cluster(bar(B_W_EMPTY + slot), par);
-        if (elect_one()) {
+    if (elect_one()) {                                  // one thread per producer warp, tight loop (no per-stage elect/syncwarp)
+      uint32_t slot = pid, par = 1;
+      int carry = pid;                                  // first stage of this producer inside the current super group
+      for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
+        int fi = carry;
+        int st = fi < G * s_pre ? fi % s_pre : fi - (G - 1) * s_pre;   // G passes over the pre stages, one over the post stages
+        for (; fi < n_flat; fi += kProducers) {
+          mbar_wait_cluster(bar(B_W_EMPTY + slot), par);
           if (crank == 0) mbar_arrive_expect_tx(bar(B_W_FULL + slot), 2 * kStageBytes);
           tma_load_2d_2sm(sbase + Smem::w + slot * kStageBytes, &wmap, 0, (st * 2 + (int)crank) * kStageRows, bar(B_W_FULL + slot));
+          slot += kProducers;
+          if (slot >= kStages) { slot -= kStages; par ^= 1; }
+          // next stage id without a division: inside the pre passes the id wraps at s_pre, after them it just continues
+          const int nf = fi + kProducers;
+          if (nf < G * s_pre) { st += kProducers; if (st >= s_pre) st -= s_pre; }
+          else st = nf - (G - 1) * s_pre;
         }
-        __syncwarp();
-        slot += kProducers;
-        if (slot >= kStages) { slot -= kStages; par ^= 1; }
+        carry = fi - n_flat;                            // the ring position continues across super groups
       }
-      carry = fi - n_flat;                              // the ring position continues across super groups
     }
+    __syncwarp();
   } else if (warp == 1) {
     if (crank == 0) {
       // ===================== MMA issuer (leader CTA only): ONE thread walks the per-tile stage program ==========
