@@ -167,7 +167,8 @@ enum {
   B_X_FULL, B_H_FULL = B_X_FULL + kMT,          // one per feature tile
   B_RDY = B_H_FULL + kMT, B_X_FREE = B_RDY + 4,
   B_LAND,                                       // non-leader CTA only: remote rows of chunk 2*i have landed (st.async bytes)
-  B_COUNT = B_LAND + kMT
+  B_OUT_FREE = B_LAND + kMT,                    // leader: the output epilogue has read lin_out's result out of the h region
+  B_COUNT
 };
 static_assert(B_COUNT <= 30, "barrier parity bits live in one 32-bit word");
 static_assert(Smem::total <= 227 * 1024, "shared memory budget");
@@ -315,6 +316,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     // chunk kc is produced by CTA kc % 2; in ASYNC mode even chunks need one more arrival: the relay of the non-leader CTA
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_RDY + i), kEpiWarps + ((ASYNC && (i & 1) == 0) ? 1 : 0));
     for (int i = 0; i < kMT; ++i) mbar_init(bar(B_LAND + i), kEpiWarps);
+    mbar_init(bar(B_OUT_FREE), 2);
     mbar_init(bar(B_X_FREE), 2 * kEpiWarps);
     fence_barrier_init();
   }
@@ -392,6 +394,13 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               MPROF_ADD(5);
             }
             const int st_beg = seg < G ? 0 : s_pre, st_end = seg < G ? s_pre : n_stages;
+            if (seg == 0 && sg != pair_id) {
+              // The previous super group's output epilogue (two warps of this CTA) reads lin_out's result from h tile 0; the first
+              // fc_0 of this super group only waits for a chunk signalled by the OTHER CTA's warps (odd-chunk-first order).  In
+              // practice that is thousands of cycles later; this wait (a few hundred cycles after lin_out at most) makes it explicit.
+              mbar_wait(bar(B_OUT_FREE), (ph >> B_OUT_FREE) & 1u);
+              ph ^= (1u << B_OUT_FREE);
+            }
             uint2 cur = prog[st_beg];
             for (int st = st_beg; st < st_end; ++st) {
               const uint2 nxt = prog[st + 1 < st_end ? st + 1 : st];     // in flight while this stage is issued
@@ -582,6 +591,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       if (crank == 0 && qd == 0) {
         uint32_t r[kNCol];
         tmem_ld<kNCol>(tlane + kHCol + hs * kNCol, r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_OUT_FREE));
         if (lane < d_out) {
           const float bias = bias_out[lane];
 #pragma unroll
