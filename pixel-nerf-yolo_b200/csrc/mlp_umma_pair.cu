@@ -165,8 +165,8 @@ struct Smem {
 enum {
   B_W_FULL = 0, B_W_EMPTY = B_W_FULL + kStages, B_IN_READY = B_W_EMPTY + kStages, B_IN_FREE,
   B_X_FULL, B_H_FULL = B_X_FULL + kMT,          // one per feature tile
-  B_RDY = B_H_FULL + kMT, B_X_FREE = B_RDY + 4,
-  B_LAND,                                       // non-leader CTA only: remote rows of chunk 2*i have landed (st.async bytes)
+  B_RDY = B_H_FULL + kMT, B_X_FREE = B_RDY + 4,  // one per feature tile: the view-mean epilogue has read x tile mt out of TMEM
+  B_LAND = B_X_FREE + kMT,                                       // non-leader CTA only: remote rows of chunk 2*i have landed (st.async bytes)
   B_OUT_FREE = B_LAND + kMT,                    // leader: the output epilogue has read lin_out's result out of the h region
   B_COUNT
 };
@@ -212,7 +212,7 @@ __device__ inline ProgEntry make_prog(const Sched& sc, int s, uint32_t sbase) {
   }
   ProgEntry e;
   e.w0 = ((b_addr >> 4) & 0x3FFFu) | (dcol << 14) | (acc << 23) | (wait_id << 25);
-  e.w1 = c1 | (c2 << 5) | (c3 << 14);
+  e.w1 = c1 | (c2 << 5) | (c3 << 14) | ((c1 | c2 | c3) ? (1u << 19) : 0u);   // bit 19: the stage has commits besides W_EMPTY
   return e;
 }
 
@@ -283,7 +283,9 @@ __device__ long long* g_prof_pair = nullptr;
 // fence.proxy.async.shared::cluster waiting for their remote rows to be performed (14.5 % of all warp-stall samples of the
 // synchronous version).  Rows landing in the leader are counted directly on the chunk barrier the MMA warp waits on; rows
 // landing in the non-leader are counted on its B_LAND barrier, and its otherwise idle warp 1 relays that to the leader.
-template <int NS, bool ASYNC>
+// PROF = true compiles the per-role cycle counters in (PNR_PROF=1 selects that instantiation); the production instantiation
+// carries none of their branches -- the single-thread MMA issue loop is sensitive to every extra instruction.
+template <int NS, bool ASYNC, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant__ CUtensorMap wmap,
                   const float* __restrict__ bias_x, const float* __restrict__ bias_h,
@@ -302,7 +304,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
   volatile uint32_t* tmem_base_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::bars + 8 * B_COUNT);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  long long* const prof = g_prof_pair ? reinterpret_cast<long long*>(smem + Smem::bars + 256) : nullptr;
+  long long* const prof = (PROF && g_prof_pair) ? reinterpret_cast<long long*>(smem + Smem::bars + 256) : nullptr;
   if (prof && threadIdx.x < 32) prof[threadIdx.x] = 0;
   auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8u * i; };
   auto lbar = [&](int i) -> uint32_t { return mapa_u32(sbase + Smem::bars + 8u * i, 0); };   // the leader's copy
@@ -317,7 +319,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_RDY + i), kEpiWarps + ((ASYNC && (i & 1) == 0) ? 1 : 0));
     for (int i = 0; i < kMT; ++i) mbar_init(bar(B_LAND + i), kEpiWarps);
     mbar_init(bar(B_OUT_FREE), 2);
-    mbar_init(bar(B_X_FREE), 2 * kEpiWarps);
+    for (int i = 0; i < kMT; ++i) mbar_init(bar(B_X_FREE + i), 2 * kEpiWarps);
     fence_barrier_init();
   }
   const int n_stages = sched_total(sch);
@@ -329,6 +331,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     while (run < 8 && i + run < n_stages && i + run != s_pre && (make_prog(sch, i + run, sbase).w0 >> 25) == 0) ++run;
     pe.w1 |= (uint32_t)run << 10;
     reinterpret_cast<ProgEntry*>(smem + Smem::prog)[i] = pe;
+    if (i == n_stages - 1) reinterpret_cast<ProgEntry*>(smem + Smem::prog)[n_stages] = pe;   // pad: the issuer prefetches entry st + 1
   }
   if (warp == 1) tmem_alloc_2sm(sbase + Smem::bars + 8 * B_COUNT, kTmemCols);
   tc_fence_before();
@@ -385,8 +388,10 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
 #define MPROF_ADD(slot_) do { if (prof) prof[slot_] += clock64() - t0__; } while (0)
         for (int sg = pair_id; sg < n_sg; sg += n_pairs) {
           for (int seg = 0; seg <= G; ++seg) {              // G pre-combine passes, then the post-combine pass
-            if (seg > 0 && seg < G) {
-              // the view-mean epilogue of the previous tile must have read x out of TMEM before lin_in overwrites it
+            const bool after_mean = seg > 0 && seg < G;
+            if (after_mean) {
+              // the view-mean epilogue of the previous tile must have read x tile 0 out of TMEM before lin_in (stage 0) overwrites
+              // it; tile 1 is first written by stage 1 (see below)
               MPROF_T0();
               mbar_wait_cluster(bar(B_X_FREE), (ph >> B_X_FREE) & 1u);
               ph ^= (1u << B_X_FREE);
@@ -402,8 +407,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               ph ^= (1u << B_OUT_FREE);
             }
             uint2 cur = prog[st_beg];
-            for (int st = st_beg; st < st_end; ++st) {
-              const uint2 nxt = prog[st + 1 < st_end ? st + 1 : st];     // in flight while this stage is issued
+            // one stage: wait for what the entry names and for the weight slot, issue the four MMAs and the commits
+            auto issue_stage = [&](int st) {
+              const uint2 nxt = prog[st + 1];               // in flight while this stage is issued (the program is padded by one entry)
               const uint32_t wait_id = cur.x >> 25;
               if (wait_id) {
                 MPROF_T0();
@@ -411,25 +417,37 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
                 mbar_wait_cluster(bar(id), (ph >> id) & 1u);
                 ph ^= (1u << id);
                 if (ASYNC) fence_proxy_async();             // rows that landed in this CTA by st.async
+                tc_fence_after();                           // the other warps' tcgen05.ld / st of this TMEM precede the MMAs below
                 MPROF_ADD(id == B_IN_READY ? 2 : 4);
               }
               {
                 MPROF_T0();
-                mbar_wait(bar(B_W_FULL + slot), wpar);
+                mbar_wait(bar(B_W_FULL + slot), wpar);      // completed by the TMA engine: no tcgen05 fence needed
                 MPROF_ADD(1);
               }
-              tc_fence_after();
               const uint64_t b_desc = bdesc_hi | (uint64_t)(cur.x & 0x3FFFu);
               const uint32_t d_col = (cur.x >> 14) & 0x1FFu;
               mma_kblock_desc_2sm(tmem_base + d_col, wdesc0 + slot * kStageStep, b_desc, idesc, (cur.x >> 23) & 1u);
               mma_commit_2sm(bar(B_W_EMPTY + slot), 3);
-              const uint32_t c1 = cur.y & 31u, c2 = (cur.y >> 5) & 31u, c3 = (cur.y >> 14) & 31u;
-              if (c1) mma_commit_2sm(bar(c1 - 1), 3);
-              if (c2) mma_commit_2sm(bar(c2 - 1), 3);
-              if (c3) mma_commit_2sm(bar(c3 - 1), 3);
+              if (cur.y & (1u << 19)) {
+                const uint32_t c1 = cur.y & 31u, c2 = (cur.y >> 5) & 31u, c3 = (cur.y >> 14) & 31u;
+                if (c1) mma_commit_2sm(bar(c1 - 1), 3);
+                if (c2) mma_commit_2sm(bar(c2 - 1), 3);
+                if (c3) mma_commit_2sm(bar(c3 - 1), 3);
+              }
               if (++slot == kStages) { slot = 0; wpar ^= 1; }
               cur = nxt;
+            };
+            int st = st_beg;
+            if (after_mean) {                               // lin_in's second stage is the first write into x tile 1
+              issue_stage(st++);
+              MPROF_T0();
+              mbar_wait_cluster(bar(B_X_FREE + 1), (ph >> (B_X_FREE + 1)) & 1u);
+              ph ^= (1u << (B_X_FREE + 1));
+              tc_fence_after();
+              MPROF_ADD(5);
             }
+            for (; st < st_end; ++st) issue_stage(st);
           }
         }
 #undef MPROF_T0
@@ -542,6 +560,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           const float bias = bias_x[sch.CL * kHidden + f];
           uint32_t v[kNCol];
           tmem_ld<kNCol>(tlane + mt * 128 + hs * kNCol, v);
+          if (g + 1 < G) {                          // x tile mt is in registers -> the next tile's lin_in / lin_z may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_X_FREE + mt)); else mbar_arrive_cluster_relaxed(lbar(B_X_FREE + mt)); }
+          }
           float* dst = xbar + ((size_t)hs * kNCol + g * PP) * kHidden + f;
 #pragma unroll
           for (int p = 0; p < PP; ++p) {
@@ -551,11 +574,6 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
             const bool ok = live && p0 + p < q.P;
             __stcg(dst + (size_t)p * kHidden, ok ? __fdiv_rn(acc, (float)NS) + bias : 0.f);
           }
-        }
-        if (g + 1 < G) {                            // TMEM reads done -> the next tile's lin_in may overwrite x
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_X_FREE)); else mbar_arrive_cluster_relaxed(lbar(B_X_FREE)); }
         }
       }
       // ================= post-combine: one tile of 64 columns per CTA (column j = g*PP + p of the tiles above)
@@ -752,7 +770,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (g_prof_pair && threadIdx.x < 32) g_prof_pair[(size_t)blockIdx.x * 32 + threadIdx.x] = prof[threadIdx.x];
+  if (PROF && g_prof_pair && threadIdx.x < 32) g_prof_pair[(size_t)blockIdx.x * 32 + threadIdx.x] = prof[threadIdx.x];
   cluster_sync_all();                    // no CTA exits (or frees TMEM) while the pair may still touch it
   if (warp == 1) tmem_dealloc_2sm(tmem_base, kTmemCols);
 }
@@ -786,7 +804,7 @@ int pair_stages(const pnr_mlp_params* p, int proj) {
 }
 int pair_pack(const pnr_mlp_params* p, uint8_t* stream, int proj, cudaStream_t st) {
   pair::Sched s = pair_sched(p, proj);
-  PNR_REQUIRE(pair::sched_total(s) <= pair::kMaxStages, PNR_ERR_UNSUPPORTED, "pair_pack: %d stages exceed the stage program", pair::sched_total(s));
+  PNR_REQUIRE(pair::sched_total(s) < pair::kMaxStages, PNR_ERR_UNSUPPORTED, "pair_pack: %d stages exceed the stage program (one padding entry is needed)", pair::sched_total(s));
   pair::pack_stages_kernel<<<pair::sched_total(s) * 2, 256, 0, st>>>(*p, s, stream);
   PNR_CHECK_LAUNCH("pair::pack_stages_kernel");
   return PNR_OK;
@@ -849,7 +867,8 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   }
 #define PNR_LAUNCH_PAIR(NSV)                                                                                     \
   case NSV: {                                                                                                    \
-    auto kern = async_x ? pair::field_pair_kernel<NSV, true> : pair::field_pair_kernel<NSV, false>;             \
+    auto kern = async_x ? (prof_dev ? pair::field_pair_kernel<NSV, true, true> : pair::field_pair_kernel<NSV, true, false>) \
+                        : pair::field_pair_kernel<NSV, false, false>;                                           \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::Smem::total); \
     PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
     cudaLaunchConfig_t cfg = {};                                                                                 \
