@@ -380,7 +380,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       const long long t_role0 = prof ? clock64() : 0;
       if (elect_one()) {
         uint32_t slot = 0, wpar = 0, ph = 0;
+        uint32_t full_bar = bar(B_W_FULL), empty_bar = bar(B_W_EMPTY);      // running addresses of the current ring slot's barriers
         const uint64_t wdesc0 = smem_desc(sbase + Smem::w);
+        uint64_t a_desc = wdesc0;                                           // ... and of its A descriptor
         const uint64_t bdesc_hi = smem_desc(0);
         constexpr uint64_t kStageStep = kStageBytes >> 4;
         const uint2* prog = reinterpret_cast<const uint2*>(smem + Smem::prog);
@@ -422,20 +424,21 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               }
               {
                 MPROF_T0();
-                mbar_wait(bar(B_W_FULL + slot), wpar);      // completed by the TMA engine: no tcgen05 fence needed
+                mbar_wait(full_bar, wpar);                  // completed by the TMA engine: no tcgen05 fence needed
                 MPROF_ADD(1);
               }
               const uint64_t b_desc = bdesc_hi | (uint64_t)(cur.x & 0x3FFFu);
               const uint32_t d_col = (cur.x >> 14) & 0x1FFu;
-              mma_kblock_desc_2sm(tmem_base + d_col, wdesc0 + slot * kStageStep, b_desc, idesc, (cur.x >> 23) & 1u);
-              mma_commit_2sm(bar(B_W_EMPTY + slot), 3);
+              mma_kblock_desc_2sm(tmem_base + d_col, a_desc, b_desc, idesc, (cur.x >> 23) & 1u);
+              mma_commit_2sm(empty_bar, 3);
               if (cur.y & (1u << 19)) {
                 const uint32_t c1 = cur.y & 31u, c2 = (cur.y >> 5) & 31u, c3 = (cur.y >> 14) & 31u;
                 if (c1) mma_commit_2sm(bar(c1 - 1), 3);
                 if (c2) mma_commit_2sm(bar(c2 - 1), 3);
                 if (c3) mma_commit_2sm(bar(c3 - 1), 3);
               }
-              if (++slot == kStages) { slot = 0; wpar ^= 1; }
+              if (++slot == kStages) { slot = 0; wpar ^= 1; full_bar = bar(B_W_FULL); empty_bar = bar(B_W_EMPTY); a_desc = wdesc0; }
+              else { full_bar += 8; empty_bar += 8; a_desc += kStageStep; }
               cur = nxt;
             };
             int st = st_beg;
