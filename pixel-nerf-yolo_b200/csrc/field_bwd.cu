@@ -139,18 +139,31 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 
 // Same contract on the tensor cores: TF32 operands (10-bit mantissa, round-to-nearest), fp32 accumulate, legacy
 // mma.sync.m16n8k8 -- the optional fast arithmetic of the training path (PNR_SCENE_TRAIN_TF32).  128x128x16 tiles, 8 warps
-// of 64x32; operands are rounded once when they are staged in shared memory (rows padded to 132 floats: conflict-free
-// fragment loads).
+// of 64x32; operands are rounded once when they are staged in shared memory and read back with ldmatrix.
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-constexpr int TK = 16, TP = 132;
+constexpr int TK = 16, TKP = 20;   // k-tile and padded row pitch in floats (80 B: the 8 row addresses of an ldmatrix hit 32 distinct banks)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const float* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 template <bool A_T, bool B_T>
 __global__ void __launch_bounds__(256) sgemm_tf32_kernel(const GemmArgs g) {
-  __shared__ __align__(16) float As[TK][TP];
-  __shared__ __align__(16) float Bs[TK][TP];
+  // Each operand is staged the way it arrives from global memory, so the staging stores are contiguous and conflict-free:
+  //  * k-contiguous operand (A of X W^T and dY W; B = W of X W^T): [row][k], pitch TKP; an 8x8 b16 ldmatrix tile = 8 rows x 4
+  //    tf32 values, so one ldmatrix.x4 delivers a whole m16k8 A fragment (or the B fragments of two n8 tiles);
+  //  * row-contiguous operand (the transposed ones of dY W and dY^T X): [k][row], pitch TP; fragments by 32-bit loads.
+  constexpr int TP = 136;            // [k][row] pitch: 8 banks (mod 32) per k row -> the (k = lane % 4, row = lane / 4) loads are conflict-free
+  constexpr int kBufFloats = BM * TKP > TK * TP ? BM * TKP : TK * TP;
+  __shared__ __align__(16) float As_raw[2][kBufFloats];
+  __shared__ __align__(16) float Bs_raw[2][kBufFloats];
+  auto As_rk = [&](int buf, int row, int k) -> float* { return &As_raw[buf][row * TKP + k]; };
+  auto As_kr = [&](int buf, int k, int row) -> float* { return &As_raw[buf][k * TP + row]; };
+  auto Bs_rk = [&](int buf, int row, int k) -> float* { return &Bs_raw[buf][row * TKP + k]; };
+  auto Bs_kr = [&](int buf, int k, int row) -> float* { return &Bs_raw[buf][k * TP + row]; };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tq = lane & 3;
   const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
@@ -177,8 +190,9 @@ __global__ void __launch_bounds__(256) sgemm_tf32_kernel(const GemmArgs g) {
       for (int e = 0; e < 8; ++e) v[e] = (row_ok && c + e < c_end) ? p[e] : 0.f;
     }
   };
-  for (long long k0 = kbeg; k0 < kend; k0 += TK) {
-    float a[8], b[8];
+  // register-prefetched, double-buffered main loop: the global loads of tile k0 + TK are in flight while tile k0 is multiplied
+  float a[8], b[8];
+  auto gload = [&](long long k0) {
     if (A_T) {          // i contiguous: thread -> (k = tid / 16, 8 consecutive i)
       const long long k = k0 + (tid >> 4);
       load8(g.A, k, g.lda, i0 + (tid & 15) * 8, g.I, k < kend, a);
@@ -193,6 +207,8 @@ __global__ void __launch_bounds__(256) sgemm_tf32_kernel(const GemmArgs g) {
       const long long j = j0 + (tid >> 1);
       load8(g.B, j, g.ldb, k0 + (tid & 1) * 8, kend, j < g.J, b);
     }
+  };
+  auto sstore = [&](int buf) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (g.relu_a) a[e] = fmaxf(a[e], 0.f);
@@ -200,37 +216,51 @@ __global__ void __launch_bounds__(256) sgemm_tf32_kernel(const GemmArgs g) {
       a[e] = to_tf32(a[e]);
       b[e] = to_tf32(b[e]);
     }
-    if (A_T) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) As[tid >> 4][(tid & 15) * 8 + e] = a[e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) As[(tid & 1) * 8 + e][tid >> 1] = a[e];
+    {
+      float4* d = reinterpret_cast<float4*>(A_T ? As_kr(buf, tid >> 4, (tid & 15) * 8) : As_rk(buf, tid >> 1, (tid & 1) * 8));
+      d[0] = make_float4(a[0], a[1], a[2], a[3]); d[1] = make_float4(a[4], a[5], a[6], a[7]);
     }
-    if (!B_T) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) Bs[tid >> 4][(tid & 15) * 8 + e] = b[e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) Bs[(tid & 1) * 8 + e][tid >> 1] = b[e];
+    {
+      float4* d = reinterpret_cast<float4*>(!B_T ? Bs_kr(buf, tid >> 4, (tid & 15) * 8) : Bs_rk(buf, tid >> 1, (tid & 1) * 8));
+      d[0] = make_float4(b[0], b[1], b[2], b[3]); d[1] = make_float4(b[4], b[5], b[6], b[7]);
     }
-    __syncthreads();
+  };
+  // ldmatrix lane roles: lane = 8 * mat + r
+  const int lm = lane >> 3, lr = lane & 7;
+  const int a_row = lr + (lm & 1) * 8, a_k = (lm >> 1) * 4;      // A: matrices (rows 0-7, k), (rows 8-15, k), (rows 0-7, k+4), (rows 8-15, k+4)
+  const int b_row = lr + (lm >> 1) * 8, b_k = (lm & 1) * 4;      // B: (n 0-7, k), (n 0-7, k+4), (n 8-15, k), (n 8-15, k+4)
+  int buf = 0;
+  if (kbeg < kend) { gload(kbeg); sstore(0); }
+  __syncthreads();
+  for (long long k0 = kbeg; k0 < kend; k0 += TK, buf ^= 1) {
+    const bool more = k0 + TK < kend;
+    if (more) gload(k0 + TK);
 #pragma unroll
     for (int ks = 0; ks < TK; ks += 8) {
-      uint32_t af[4][4], bf[4][2];
+      uint32_t af[4][4], bf[2][4];
+      if (A_T) {
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        const int m = wm + mi * 16 + gq;
-        af[mi][0] = __float_as_uint(As[ks + tq][m]);
-        af[mi][1] = __float_as_uint(As[ks + tq][m + 8]);
-        af[mi][2] = __float_as_uint(As[ks + tq + 4][m]);
-        af[mi][3] = __float_as_uint(As[ks + tq + 4][m + 8]);
+        for (int mi = 0; mi < 4; ++mi) {
+          const int m = wm + mi * 16 + gq;
+          af[mi][0] = __float_as_uint(*As_kr(buf, ks + tq, m));
+          af[mi][1] = __float_as_uint(*As_kr(buf, ks + tq, m + 8));
+          af[mi][2] = __float_as_uint(*As_kr(buf, ks + tq + 4, m));
+          af[mi][3] = __float_as_uint(*As_kr(buf, ks + tq + 4, m + 8));
+        }
+      } else {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) ldmatrix_x4(af[mi], As_rk(buf, wm + mi * 16 + a_row, ks + a_k));
       }
+      if (!B_T) {
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int n = wn + ni * 8 + gq;
-        bf[ni][0] = __float_as_uint(Bs[ks + tq][n]);
-        bf[ni][1] = __float_as_uint(Bs[ks + tq + 4][n]);
+        for (int ni = 0; ni < 4; ++ni) {
+          const int n = wn + ni * 8 + gq;
+          bf[ni >> 1][(ni & 1) * 2] = __float_as_uint(*Bs_kr(buf, ks + tq, n));
+          bf[ni >> 1][(ni & 1) * 2 + 1] = __float_as_uint(*Bs_kr(buf, ks + tq + 4, n));
+        }
+      } else {
+#pragma unroll
+        for (int np = 0; np < 2; ++np) ldmatrix_x4(bf[np], Bs_rk(buf, wn + np * 16 + b_row, ks + b_k));
       }
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
@@ -238,8 +268,10 @@ __global__ void __launch_bounds__(256) sgemm_tf32_kernel(const GemmArgs g) {
         for (int ni = 0; ni < 4; ++ni)
           asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                        : "+f"(acc[mi][ni][0]), "+f"(acc[mi][ni][1]), "+f"(acc[mi][ni][2]), "+f"(acc[mi][ni][3])
-                       : "r"(af[mi][0]), "r"(af[mi][1]), "r"(af[mi][2]), "r"(af[mi][3]), "r"(bf[ni][0]), "r"(bf[ni][1]));
+                       : "r"(af[mi][0]), "r"(af[mi][1]), "r"(af[mi][2]), "r"(af[mi][3]), "r"(bf[ni >> 1][(ni & 1) * 2]),
+                         "r"(bf[ni >> 1][(ni & 1) * 2 + 1]));
     }
+    if (more) sstore(buf ^ 1);
     __syncthreads();
   }
 #pragma unroll
