@@ -692,12 +692,6 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         const int pass = fill % n_pass;
         const int kp = sch.KBz - pass * 8 < 8 ? sch.KBz - pass * 8 : 8;
         const int ch0 = sch.proj ? (fill / n_pass) * kHidden : pass * 512;   // projected maps: lin_z[b]'s own 512-channel slice
-        {
-          PPROF_T0();
-          mbar_wait_cluster(bar(B_IN_FREE), par_free);
-          if (gw == 0) PPROF_ADD(17);
-        }
-        par_free ^= 1;
         // ---- 4 taps x 1 KiB per column, two columns in flight per warp (the loads are L2 hits with ~1-2 k cycles of
         // latency under the weight stream's load; one column at a time left the tensor cores waiting for the gather)
         const bool act = (lane >> 2) < kp;
@@ -708,7 +702,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           for (int k = 0; k < 4; ++k) {
             const int off = __shfl_sync(0xffffffffu, tp.off[k], i);
             w[k] = __shfl_sync(0xffffffffu, tp.w[k], i);
+#ifdef PNR_DIAG_NOGATHER   // timing diagnostic only: no tap loads
+            if (false) {
+#else
             if (off >= 0 && act) {
+#endif
               const uint4* src = reinterpret_cast<const uint4*>(fl0 + vb + off);
               r[2 * k] = __ldg(src); r[2 * k + 1] = __ldg(src + 1);
             } else {
@@ -749,8 +747,14 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         {
           uint4 ra[8], rb[8];
           float wa[4], wb[4];
-          load_col(0, ra, wa);
-          load_col(1, rb, wb);
+          load_col(0, ra, wa);                       // the first two columns' loads go out BEFORE the operand buffers are free:
+          load_col(1, rb, wb);                       // they only fill registers
+          {
+            PPROF_T0();
+            mbar_wait_cluster(bar(B_IN_FREE), par_free);
+            if (gw == 0) PPROF_ADD(17);
+          }
+          par_free ^= 1;
           if (fill == 0) {                           // the sin/cos work runs under the first loads' latency
 #pragma unroll 1
             for (int i = 0; i < 16; ++i) zfeat_col(i);
