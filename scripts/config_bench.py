@@ -111,8 +111,36 @@ def config5():
                               "rays_per_s": round(n / (ms * 1e-3)), "algorithmic_TFLOPs": round(fl / (ms * 1e-3) / 1e12, 1)}))
 
 
-which = [int(a) for a in sys.argv[1:]] or [3, 4, 5]
+def yolo():
+    """conf/exp/yolo.conf shape: YoloRenderer, 128 samples per ray, 3 anchors x 7 values, 3 x 1792 x 80 x 80 maps (synthetic), 640x640 image."""
+    import copy
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.model import make_model
+    from pixel_nerf_yolo_b200.render import YoloRenderer
+    conf = copy.deepcopy(H.MODEL_CONF)
+    conf["mlp_coarse"].update({"d_out": 7, "num_scales": 1, "num_anchors_per_scale": 3, "yolo": True})
+    conf["mlp_fine"] = {"type": "empty"}
+    conf["encoder"] = {"backbone": "custom", "pretrained": False, "num_layers": 4, "index_padding": "zeros"}
+    scene = H.make_scene_dict(num_objs=1, num_views=3, feat=80, size=640, C=1792)
+    net = make_model(ConfigTree.from_dict(conf)).eval()
+    net.mlp_coarse.load_state_dict(synth.mlp_state(31, d_out=21, d_latent=1792))
+    net = net.to(dev)
+    net.num_objs, net.num_views_per_obj = 1, 3
+    net.encoder.set_latent(scene["latent"].to(dev))
+    net.set_cameras(torch.linalg.inv(scene["poses"][0]).to(dev), scene["focal"].to(dev), scene["image_wh"])
+    r = YoloRenderer(128, 128, 1, 3)
+    r.bind_parallel(net)
+    rays = synth.target_rays(640)[0, ::10].contiguous().to(dev)          # 40 960 rays
+    ms = timed(lambda: r(rays), reps=3)
+    h, c, d_in = 512, 1792, 42
+    per_pt = 2 * (3 * (d_in * h + 3 * (c * h + 2 * h * h)) + 2 * 2 * h * h + h * 21)
+    print(json.dumps({"config": "yolo", "workload": "YoloRenderer, 40960 rays x 128 samples, 3 views, 3x1792x80x80 maps, d_out 21",
+                      "ms": round(ms, 1), "rays_per_s": round(rays.shape[0] / (ms * 1e-3)),
+                      "algorithmic_TFLOPs": round(per_pt * 128 * rays.shape[0] / (ms * 1e-3) / 1e12, 1)}))
+
+
+which = [a if a == "yolo" else int(a) for a in sys.argv[1:]] or [3, 4, 5, "yolo"]
 for w in which:
-    {3: config3, 4: config4, 5: config5}[w]()
+    {3: config3, 4: config4, 5: config5, "yolo": yolo}[w]()
     if w == 3:
         config3("tf32")
