@@ -4,22 +4,27 @@
 // the two SMs of a cluster of 2:  M = 256 features (128 per CTA), N = 128 columns (64 per CTA: each CTA gathers and
 // owns its own tile of 64 columns = PP points x NS views), K = 16.
 //   * per MMA each CTA reads 4 KiB of weights + 2 KiB of activations from its own shared memory for 4x the MACs of
-//     the single-CTA N=64 MMA -- the shared-memory traffic per MAC that bounds mlp_umma.cu drops by 4, and N=128
-//     runs the tensor pipe at its full rate (scripts/umma_bench.py);
+//     the single-CTA N=64 MMA, and N=128 runs the tensor pipe at its full rate (scripts/umma_bench.py);
 //   * each CTA streams only ITS half (128 rows) of every 256-row weight slab (tensor-map TMA, cta_group::2, completion
-//     on the leader's mbarrier), so the weight fill per SM per column halves as well;
+//     on the leader's mbarrier);
 //   * TMEM per CTA: x^T = 2 feature tiles x 128 columns (cols [0,256)), h^T likewise (cols [256,512)).
 // The price: D rows are FEATURES (CTA c holds features 256*mt + 128*c + lane of all 128 columns) while the B operand
 // needs COLUMNS (CTA c holds the rows of its own 64 columns for all K).  So every epilogue unit sends half of its
 // bf16 output to the peer CTA's shared memory: values are transposed 8x8 across lanes (shuffles) into 16-byte chunks
-// = 8 consecutive K elements of one operand row, and stored with st.shared / st.shared::cluster.  Epilogue warp
-// (quadrant qd, half hs) handles the 64 columns of CTA hs, so a warp's stores all go to one CTA.
+// = 8 consecutive K elements of one operand row; the peer's rows leave as st.async (counted on a barrier of the
+// destination CTA), the own rows as st.shared.  Epilogue warp (quadrant qd, half hs) handles 32 columns of both tiles.
+//
+// Warp roles (16 warps per CTA): 0, 12, 13 weight producers (one elected thread each); 1 = MMA issuer in the leader CTA
+// (ONE elected thread, lean per-stage loop) / relay in the other CTA; 2, 3, 14, 15 gather; 4..11 epilogue.
 //
 // Hand-offs (L = leader CTA 0; "mc" = tcgen05.commit.cta_group::2 multicast to both CTAs):
-//   W_FULL[s]  @L   : leader producer's expect_tx(32 KiB) + TMA bytes of both CTAs     W_EMPTY[s] @both : mc
-//   IN_READY   @L   : gather warps of both CTAs (remote arrive)                        IN_FREE    @both : mc
-//   AX/AH_READY[i] @L : the 8 epilogue warps of CTA i (ring slot i is always written by CTA i)   *_FREE[i] @both : mc
-//   X_FULL, H_FULL @both : mc
+//   W_FULL[s]  @L    : leader producer's expect_tx(32 KiB) + TMA bytes of both CTAs      W_EMPTY[s] @both : mc
+//   IN_READY   @L    : gather warps of both CTAs (remote arrive)                         IN_FREE    @both : mc
+//   RDY[kc]    @L    : chunk kc (produced by CTA kc % 2) is in place in both CTAs: the producing warps' arrivals, plus
+//                      the st.async bytes landing in L (odd kc) or the relay's arrival for bytes that landed in CTA 1 (even kc)
+//   LAND[mt]   @CTA1 : st.async bytes of chunk 2*mt from L have landed (+ L's warps' remote arrive.expect_tx)
+//   X_FULL[mt], H_FULL[mt] @both : mc, one per feature tile        X_FREE[mt] @L : view-mean epilogue has read x tile mt
+//   OUT_FREE   @L    : the output epilogue has read lin_out's result
 #include "pnr_common.cuh"
 #include "umma.cuh"
 #include <cuda.h>
