@@ -229,6 +229,32 @@ int pnr_sample_fine_depth_backward(const float* z_sorted, const float* d_z_sorte
                                    const float* gauss, const float* rays, float* d_depth, int B, int K, int Kfd,
                                    float depth_std, void* stream);
 
+/* ---- the whole render in one call: NeRFRenderer.forward (src/render/nerf.py:257-309) ----------------------------- */
+/* sample_coarse -> field (coarse MLP) -> composite -> sample_fine + sample_fine_depth + sort -> field (fine MLP) ->
+ * composite, enqueued back to back on `stream` (bf16 tensor-core path).  rays (SB*B, 8); noise as for the stage calls;
+ * outputs rgb (SB*B,3), depth (SB*B), optional weights (SB*B,K); fine outputs unused when n_fine == 0; mlp_fine may be
+ * NULL (the coarse network renders the fine pass, models.py:291).  workspace: pnr_render_workspace_bytes(), 256-byte
+ * aligned (sample depths, field values, view-mean scratch). */
+typedef struct pnr_render_args {
+  const pnr_scene* scene;
+  const float* rays; int32_t B;                    /* rays per object */
+  const float* steps;                              /* linspace(0, 1 - 1/Kc, Kc), see pnr_sample_coarse */
+  const float* noise_coarse; const float* noise_u; const float* noise_jitter; const float* noise_gauss;
+  const pnr_mlp_params* mlp_coarse; const void* packed_coarse;
+  const pnr_mlp_params* mlp_fine;   const void* packed_fine;
+  int32_t n_coarse, n_fine, n_fine_depth;
+  float depth_std;
+  int32_t white_bkgd, lindisp, precision, num_freqs;
+  float freq_factor;
+  float* rgb_coarse; float* depth_coarse; float* weights_coarse;
+  float* rgb_fine;   float* depth_fine;   float* weights_fine;
+  void* workspace; size_t workspace_bytes;
+  void* field_events[4];                           /* optional cudaEvent_t: recorded before / after the coarse and the fine
+                                                      field-kernel launch (measurement hook of bench.py); NULL = none */
+} pnr_render_args;
+size_t pnr_render_workspace_bytes(const pnr_render_args* args);
+int pnr_render_forward(const pnr_render_args* args, void* stream);
+
 /* ResnetFC.forward as a stand-alone operator (src/model/resnetfc.py:134-186), fp32 arithmetic.
  * zx (rows, d_latent + d_in) fp32, rows ordered (object, view, point) with NS views and P points per
  * object (combine_inner_dims = (NS, P)); out (rows / NS, d_out) raw lin_out values. */

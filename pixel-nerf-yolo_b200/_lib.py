@@ -32,6 +32,7 @@ EXPORTS = [
     "pnr_field_tape_bytes", "pnr_field_forward_train", "pnr_field_backward_workspace_bytes", "pnr_field_backward",
     "pnr_composite_backward", "pnr_sample_fine_depth_backward", "pnr_pyramid_pack", "pnr_gen_rays", "pnr_yolo_reduce", "pnr_image_output", "pnr_rgb_loss",
     "pnr_mlp_pack_projected_bytes", "pnr_mlp_pack_projected", "pnr_project_features",
+    "pnr_render_workspace_bytes", "pnr_render_forward",
 ]
 
 
@@ -62,6 +63,20 @@ class MlpGrads(C.Structure):
                 ("lin_out_b", C.c_void_p), ("fc0_w", C.c_void_p * 8), ("fc0_b", C.c_void_p * 8),
                 ("fc1_w", C.c_void_p * 8), ("fc1_b", C.c_void_p * 8), ("linz_w", C.c_void_p * 8),
                 ("linz_b", C.c_void_p * 8)]
+
+
+class RenderArgs(C.Structure):
+    """pnr_render_args: NeRFRenderer.forward as one C call."""
+    _fields_ = [("scene", C.POINTER(Scene)), ("rays", C.c_void_p), ("B", C.c_int32), ("steps", C.c_void_p),
+                ("noise_coarse", C.c_void_p), ("noise_u", C.c_void_p), ("noise_jitter", C.c_void_p), ("noise_gauss", C.c_void_p),
+                ("mlp_coarse", C.POINTER(MlpParams)), ("packed_coarse", C.c_void_p),
+                ("mlp_fine", C.POINTER(MlpParams)), ("packed_fine", C.c_void_p),
+                ("n_coarse", C.c_int32), ("n_fine", C.c_int32), ("n_fine_depth", C.c_int32), ("depth_std", C.c_float),
+                ("white_bkgd", C.c_int32), ("lindisp", C.c_int32), ("precision", C.c_int32), ("num_freqs", C.c_int32),
+                ("freq_factor", C.c_float),
+                ("rgb_coarse", C.c_void_p), ("depth_coarse", C.c_void_p), ("weights_coarse", C.c_void_p),
+                ("rgb_fine", C.c_void_p), ("depth_fine", C.c_void_p), ("weights_fine", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("field_events", C.c_void_p * 4)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -124,6 +139,9 @@ def load() -> C.CDLL:
     lib.pnr_mlp_pack_projected_bytes.restype = C.c_size_t
     lib.pnr_mlp_pack_projected.argtypes = [C.POINTER(MlpParams), vp, vp]
     lib.pnr_project_features.argtypes = [C.POINTER(MlpParams), vp, C.c_longlong, vp, vp, C.c_size_t, vp]
+    lib.pnr_render_workspace_bytes.argtypes = [C.POINTER(RenderArgs)]
+    lib.pnr_render_workspace_bytes.restype = C.c_size_t
+    lib.pnr_render_forward.argtypes = [C.POINTER(RenderArgs), vp]
     lib.pnr_image_output.argtypes = [vp, vp, vp, vp, C.c_longlong, f32, f32, vp]
     lib.pnr_rgb_loss.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp]
     lib.pnr_yolo_reduce.argtypes = [vp, vp, i32, i32, i32, vp]

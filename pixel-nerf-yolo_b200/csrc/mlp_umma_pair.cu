@@ -331,10 +331,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
   const int s_pre = sched_pre(sch);                 // stages [0, s_pre) run per pre-combine tile, [s_pre, n_stages) per super group
   const int n_flat = G * s_pre + (n_stages - s_pre);   // weight stages one super group consumes
   for (int i = threadIdx.x; i < n_stages; i += kThreads) {
-    ProgEntry pe = make_prog(sch, i, sbase);
-    int run = 1;
-    while (run < 8 && i + run < n_stages && i + run != s_pre && (make_prog(sch, i + run, sbase).w0 >> 25) == 0) ++run;
-    pe.w1 |= (uint32_t)run << 10;
+    const ProgEntry pe = make_prog(sch, i, sbase);
     reinterpret_cast<ProgEntry*>(smem + Smem::prog)[i] = pe;
     if (i == n_stages - 1) reinterpret_cast<ProgEntry*>(smem + Smem::prog)[n_stages] = pe;   // pad: the issuer prefetches entry st + 1
   }

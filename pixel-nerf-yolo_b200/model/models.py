@@ -310,6 +310,16 @@ class PixelNeRFNet(torch.nn.Module):
             lat = lat.detach()
         return lat.float().permute(0, 2, 3, 1).contiguous()
 
+    def fused_render_ready(self) -> bool:
+        """True when NeRFRenderer can hand the whole forward to ``pnr_render_forward`` (one C call): bf16 tensor-core path,
+        NeRF head, one scene for both passes (no per-network lin_z pre-projection of wide latents)."""
+        if self.precision != "bf16" or self.yolo:
+            return False
+        proj = self.project_wide_latent
+        if proj is None:
+            proj = self.mlp_coarse.d_latent > self.mlp_coarse.d_hidden
+        return not proj
+
     def field_from_rays(self, rays, z, coarse=True, sb=1):
         """Renderer fast path: evaluate the field at o + z*d for rays (SB*B, 8), z (SB*B, K) without ever
         materialising the points (nerf.py:191-222 folded into the kernel's point fetch).  -> (SB*B, K, 4)."""

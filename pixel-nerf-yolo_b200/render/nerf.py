@@ -131,6 +131,7 @@ class NeRFRenderer(torch.nn.Module):
         self.register_buffer("iter_idx", torch.tensor(0, dtype=torch.long), persistent=True)
         self.register_buffer("last_sched", torch.tensor(0, dtype=torch.long), persistent=True)
         self.noise_override = None      # optional dict(coarse, fine_u, fine_jitter, depth) of device tensors
+        self.field_events = None        # optional 4 torch.cuda.Event (timing on): recorded around the two field-kernel launches
         self.last_launches = 0          # kernels launched by the last forward (bench.py's gpu_launches)
 
     # ---- stage wrappers (public so the parity tests can drive each reference method) -------------------
@@ -222,6 +223,8 @@ class NeRFRenderer(torch.nn.Module):
         nz = self.noise_override or {}
         if torch.is_grad_enabled() and hasattr(model, "_wants_grad") and model._wants_grad(True):
             return self._forward_train(model, rays.detach(), sb, want_weights, nz)
+        if getattr(model, "fused_render_ready", lambda: False)() and rays.shape[0] > 0:
+            return self._forward_single_call(model, rays, sb, want_weights, nz)
         with torch.no_grad():
             z_coarse = self.sample_coarse(rays, nz.get("coarse"))
             out_c = self._field(model, rays, z_coarse, True, sb)
@@ -234,6 +237,72 @@ class NeRFRenderer(torch.nn.Module):
                 out_f = self._field(model, rays, z_all, False, sb)
                 fine = self.composite_values(out_f, z_all, rays, want_weights=want_weights)
                 outputs.fine = self._format_outputs(fine, sb, want_weights)
+        return outputs
+
+    def _forward_single_call(self, model, rays, sb, want_weights, nz):
+        """Inference: the whole of nerf.py:257-309 as ONE C-ABI call (``pnr_render_forward``).  Noise is drawn with the
+        reference's four torch calls in the reference's order (nerf.py:117,141,147,164)."""
+        import ctypes as C
+        lib = _lib.load()
+        dev = rays.device
+        Bt = rays.shape[0]
+        kc, kf, kfd = self.n_coarse, self.n_fine - self.n_fine_depth, self.n_fine_depth
+        fine = self.using_fine and self.n_fine > 0
+        with torch.no_grad():
+            noise_c = nz.get("coarse")
+            if noise_c is None:
+                noise_c = torch.rand(Bt, kc, device=dev, dtype=torch.float32)
+            u = jitter = gauss = None
+            if fine:
+                u, jitter, gauss = nz.get("fine_u"), nz.get("fine_jitter"), nz.get("depth")
+                if kf > 0:
+                    if u is None:
+                        u = torch.rand(Bt, kf, dtype=torch.float32, device=dev)
+                    if jitter is None:
+                        jitter = torch.rand_like(u)
+                if kfd > 0 and gauss is None:
+                    gauss = torch.randn(Bt, kfd, dtype=torch.float32, device=dev)
+            cont = lambda t: None if t is None else t.contiguous()
+            noise_c, u, jitter, gauss = cont(noise_c), cont(u), cont(jitter), cont(gauss)
+            steps = self._steps(dev)
+            sc, keep = model._scene(fp32_maps=False)
+            mc, mf = model.mlp_coarse, model.mlp_fine
+            a = _lib.RenderArgs()
+            a.scene, a.rays, a.B = C.pointer(sc), rays.data_ptr(), Bt // sb
+            a.steps, a.noise_coarse = steps.data_ptr(), noise_c.data_ptr()
+            a.noise_u, a.noise_jitter, a.noise_gauss = _lib.ptr(u), _lib.ptr(jitter), _lib.ptr(gauss)
+            cpc = mc.c_params()
+            a.mlp_coarse, a.packed_coarse = C.pointer(cpc), mc.packed().data_ptr()
+            cpf = None
+            if mf is not None:
+                cpf = mf.c_params()
+                a.mlp_fine, a.packed_fine = C.pointer(cpf), mf.packed().data_ptr()
+            a.n_coarse, a.n_fine, a.n_fine_depth = kc, (self.n_fine if fine else 0), (kfd if fine else 0)
+            a.depth_std, a.white_bkgd, a.lindisp = float(self.depth_std), int(bool(self.white_bkgd)), int(bool(self.lindisp))
+            a.precision, a.num_freqs, a.freq_factor = _lib.PREC_BF16, model.code.num_freqs, float(model.code.freq_factor)
+            f32 = dict(device=dev, dtype=torch.float32)
+            rgb_c, depth_c = torch.empty(Bt, 3, **f32), torch.empty(Bt, **f32)
+            w_c = torch.empty(Bt, kc, **f32) if want_weights else None
+            a.rgb_coarse, a.depth_coarse, a.weights_coarse = rgb_c.data_ptr(), depth_c.data_ptr(), _lib.ptr(w_c)
+            rgb_f = depth_f = w_f = None
+            if fine:
+                rgb_f, depth_f = torch.empty(Bt, 3, **f32), torch.empty(Bt, **f32)
+                w_f = torch.empty(Bt, kc + self.n_fine, **f32) if want_weights else None
+                a.rgb_fine, a.depth_fine, a.weights_fine = rgb_f.data_ptr(), depth_f.data_ptr(), _lib.ptr(w_f)
+            nbytes = lib.pnr_render_workspace_bytes(a)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+            if self.field_events is not None:            # measurement hook (bench.py): events must exist before C records them
+                for i, ev in enumerate(self.field_events[:4 if fine else 2]):
+                    ev.record()
+                    a.field_events[i] = ev.cuda_event
+            with torch.cuda.device(dev):
+                rc = lib.pnr_render_forward(a, _lib.stream_ptr(dev))
+            _lib.check(rc, "pnr_render_forward")
+            self.last_launches = lib.pnr_last_launch_count()
+            outputs = DotMap(coarse=self._format_outputs((w_c, rgb_c, depth_c), sb, want_weights))
+            if fine:
+                outputs.fine = self._format_outputs((w_f, rgb_f, depth_f), sb, want_weights)
         return outputs
 
     def _forward_train(self, model, rays, sb, want_weights, nz):

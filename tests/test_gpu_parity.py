@@ -339,3 +339,44 @@ def test_full_image_properties(lib):
     res32 = _render_cuda(net, rays[:, sub], sub_noise)
     assert (res32.fine.rgb - res.fine.rgb[:, sub]).abs().max() < 1e-2
     assert (res32.fine.depth - res.fine.depth[:, sub]).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize("num_objs,want_weights", [(1, True), (2, False)])
+def test_single_call_render_equals_staged_path(lib, num_objs, want_weights):
+    """pnr_render_forward (the whole NeRFRenderer.forward as one C call) launches the same kernels on the same data as the
+    stage-by-stage path: bit-identical outputs, same kernel count."""
+    scene = H.make_scene_dict(num_objs=num_objs, num_views=3)
+    net = H.build_net(scene, precision="bf16")
+    rays = H.rays_subset(num_objs, 333, seed=2)
+    noise = H.make_noise(num_objs * 333, seed=6)
+    r = _renderer()
+    r.noise_override = {k: v.cuda() for k, v in noise.items()}
+    assert net.fused_render_ready()
+    with torch.no_grad():
+        a = r(net, rays.cuda(), want_weights=want_weights)
+        n_single = r.last_launches
+        net.fused_render_ready = lambda: False
+        b = r(net, rays.cuda(), want_weights=want_weights)
+        n_staged = r.last_launches
+    assert n_single == n_staged == 6
+    for lvl in ("coarse", "fine"):
+        assert torch.equal(a[lvl].rgb, b[lvl].rgb) and torch.equal(a[lvl].depth, b[lvl].depth)
+        if want_weights:
+            assert torch.equal(a[lvl].weights, b[lvl].weights)
+    # coarse-only renderer and the RNG contract: same seed -> same image on both paths
+    r2 = _renderer(n_fine=0, n_fine_depth=0)
+    with torch.no_grad():
+        torch.manual_seed(3)
+        c = r2(net, rays.cuda())
+        del net.fused_render_ready
+        torch.manual_seed(3)
+        d = r2(net, rays.cuda())
+    assert len(c.fine) == 0 and torch.equal(c.coarse.rgb, d.coarse.rgb)
+    r3 = _renderer()
+    with torch.no_grad():
+        torch.manual_seed(4)
+        e = r3(net, rays.cuda())
+        net.fused_render_ready = lambda: False
+        torch.manual_seed(4)
+        f = r3(net, rays.cuda())
+    assert torch.equal(e.fine.rgb, f.fine.rgb) and torch.equal(e.fine.depth, f.fine.depth)

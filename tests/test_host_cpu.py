@@ -59,11 +59,11 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.pnr_version() == 2
     # struct layouts agree with the header (sizes computed by the C compiler)
-    src = '#include "pixelnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu",sizeof(pnr_scene),sizeof(pnr_points),sizeof(pnr_mlp_params),sizeof(pnr_mlp_grads));}'
+    src = '#include "pixelnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu",sizeof(pnr_scene),sizeof(pnr_points),sizeof(pnr_mlp_params),sizeof(pnr_mlp_grads),sizeof(pnr_render_args));}'
     exe = os.path.join(ROOT, "pixel-nerf-yolo_b200", "csrc", "build", "sizes")
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    assert sizes == [ctypes.sizeof(_lib.Scene), ctypes.sizeof(_lib.Points), ctypes.sizeof(_lib.MlpParams), ctypes.sizeof(_lib.MlpGrads)]
+    assert sizes == [ctypes.sizeof(_lib.Scene), ctypes.sizeof(_lib.Points), ctypes.sizeof(_lib.MlpParams), ctypes.sizeof(_lib.MlpGrads), ctypes.sizeof(_lib.RenderArgs)]
 
 
 def test_no_silent_cpu_fallback():
