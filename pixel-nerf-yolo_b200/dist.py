@@ -142,3 +142,55 @@ class MultiDeviceRenderer(torch.nn.Module):
         for lvl in outs[0]:
             merged[lvl] = {k: torch.cat([o[lvl][k].to(d0, non_blocking=True) for o in outs], dim=1) for k in outs[0][lvl]}
         return merged
+
+
+class GradientSync:
+    """Data-parallel training: every rank renders its own ray batch of the same step and runs its own
+    backward; the gradients of the MLPs (and of the encoder, unless ``stop_encoder_grad``) are then averaged with ONE
+    all-reduce over a persistent flat fp32 bucket -- 28 M parameters = 113 MB, one NCCL call per step instead of one per
+    tensor.  The reference gets the same sum from ``DataParallel``'s backward (src/render/nerf.py:373-377 replicates the
+    module per call and reduces the replicas' gradients onto GPU 0), i.e. the mean over ranks of per-rank mean losses
+    equals the loss of the concatenated batch when every rank holds equally many rays.
+
+    Parameters whose ``.grad`` is None on this rank (unused this step) contribute zeros, so all ranks issue the same
+    collective.  ``sync()`` returns the number of elements reduced."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self._bucket: Optional[torch.Tensor] = None
+
+    def _flat(self) -> torch.Tensor:
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        if self._bucket is None or self._bucket.numel() != n or self._bucket.device != dev:
+            self._bucket = torch.zeros(n, dtype=torch.float32, device=dev)
+        return self._bucket
+
+    @torch.no_grad()
+    def sync(self) -> int:
+        if not self.params:
+            return 0
+        flat = self._flat()
+        views, off = [], 0
+        for p in self.params:
+            v = flat[off: off + p.numel()].view_as(p)
+            views.append(v)
+            off += p.numel()
+        have = [p.grad is not None for p in self.params]
+        if all(have):
+            torch._foreach_copy_(views, [p.grad for p in self.params])
+        else:
+            flat.zero_()
+            for v, p in zip(views, self.params):
+                if p.grad is not None:
+                    v.copy_(p.grad)
+        world = dist.get_world_size(self.group)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)          # the training path's one collective
+        flat.mul_(1.0 / world)
+        for v, p in zip(views, self.params):
+            if p.grad is None:
+                p.grad = v.clone()
+            else:
+                p.grad.copy_(v)
+        return flat.numel()
