@@ -380,3 +380,101 @@ def test_single_call_render_equals_staged_path(lib, num_objs, want_weights):
         torch.manual_seed(4)
         f = r3(net, rays.cuda())
     assert torch.equal(e.fine.rgb, f.fine.rgb) and torch.equal(e.fine.depth, f.fine.depth)
+
+
+# ------------------------------------------------------------------------------------------------ lindisp (nerf.py:121,153)
+def _lindisp_renderer():
+    r = _renderer(white_bkgd=False)
+    r.lindisp = True                      # the reference passes it as a from_conf/constructor argument (dataset property)
+    assert not r.white_bkgd
+    return r
+
+
+def test_lindisp_samplers_bit_exact_vs_reference_golden(lib):
+    """Linear-in-disparity depths (the DTU setting) with per-ray near/far: coarse samples, importance samples, depth samples
+    and the merged sorted depths equal the unmodified reference's bit for bit."""
+    from test_oracle_golden import lindisp_case
+    g, rays, nz = lindisp_case()
+    r = _lindisp_renderer()
+    rc = rays.reshape(-1, 8).cuda()
+    zc = r.sample_coarse(rc, nz["coarse"].cuda())
+    assert torch.equal(zc.cpu(), T(g["z_coarse"]))
+    z_all, dbg = r.resample(rc, zc, T(g["coarse_weights"]).reshape(-1, 64).cuda(), T(g["coarse_depth"]).reshape(-1).cuda(),
+                            nz["fine_u"].cuda(), nz["fine_jitter"].cuda(), nz["depth"].cuda(), debug=True)
+    assert torch.equal(dbg[1].cpu(), T(g["z_fine"]))
+    assert torch.equal(dbg[2].cpu(), T(g["z_depth"]))
+    merged = torch.sort(torch.cat((T(g["z_coarse"]), T(g["z_fine"]), T(g["z_depth"])), -1), -1).values
+    assert torch.equal(z_all.cpu(), merged)
+
+
+def test_lindisp_resample_matches_oracle(lib):
+    """Same as test_resample_matches_oracle at B = 2000 with lindisp: only bin flips at CDF knots are admitted."""
+    B, Kc, kf, kfd = 2000, 64, 16, 16
+    g = torch.Generator().manual_seed(77)
+    rays = H.rays_subset(1, B)[0].clone()
+    rays[:, 6] = 0.5 + 0.5 * torch.rand(B, generator=g)
+    rays[:, 7] = 1.5 + torch.rand(B, generator=g)
+    zc = O.sample_coarse(rays, torch.rand(B, Kc, generator=g), Kc, lindisp=True)
+    w = torch.rand(B, Kc, generator=g) ** 6
+    depth = 0.4 + 2.4 * torch.rand(B, generator=g)
+    u, j = torch.rand(B, kf, generator=g), torch.rand(B, kf, generator=g)
+    gz = torch.randn(B, kfd, generator=g)
+    r = _lindisp_renderer()
+    z_all, dbg = r.resample(rays.cuda(), zc.cuda(), w.cuda(), depth.cuda(), u.cuda(), j.cuda(), gz.cuda(), debug=True)
+    zf, inds = O.sample_fine(rays, w, u, j, Kc, lindisp=True, return_inds=True)
+    ok = dbg[0].cpu().long() == inds
+    assert ok.float().mean() > 1 - 1e-3
+    assert torch.equal(dbg[1].cpu()[ok], zf[ok])
+    zd = O.sample_fine_depth(rays, depth, gz, 0.01)
+    assert torch.equal(dbg[2].cpu(), zd)
+    assert torch.equal(z_all.cpu(), torch.sort(torch.cat((zc, torch.where(ok, zf, dbg[1].cpu()), zd), -1), -1).values)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_lindisp_render_matches_reference_golden(lib, precision, tol):
+    """Full NeRFRenderer.forward with lindisp=True, black background, per-ray bounds vs the unmodified reference; the
+    single-call path (pnr_render_forward) and the staged path both carry the flag."""
+    from test_oracle_golden import lindisp_case
+    g, rays, nz = lindisp_case()
+    scene = H.make_scene_dict()
+    net = H.build_net(scene, precision=precision)
+    r = _lindisp_renderer()
+    r.noise_override = {k: v.cuda() for k, v in nz.items()}
+    with torch.no_grad():
+        res = r(net, rays.cuda(), want_weights=True)
+        for lvl in ("coarse", "fine"):
+            for k in ("rgb", "depth"):
+                err = np.abs(res[lvl][k].cpu().numpy() - g[f"{lvl}_{k}"]).max()
+                assert err < tol, (lvl, k, err)
+        if precision == "fp32":
+            np.testing.assert_allclose(res.fine.weights.cpu().numpy(), g["fine_weights"], atol=1e-4)
+        else:
+            assert net.fused_render_ready()
+            net.fused_render_ready = lambda: False
+            staged = r(net, rays.cuda(), want_weights=True)
+            assert torch.equal(staged.fine.rgb, res.fine.rgb) and torch.equal(staged.fine.depth, res.fine.depth)
+
+
+def test_scheduled_resolution_is_applied_at_forward(lib):
+    """nerf.py:271-273: a renderer restored from a checkpoint renders at the resolution its last_sched buffer names."""
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    conf = {"n_coarse": 64, "n_fine": 32, "n_fine_depth": 16, "white_bkgd": True, "sched": [[2, 5], [96, 128], [48, 64]]}
+    src = NeRFRenderer.from_conf(ConfigTree.from_dict(conf))
+    src.sched_step(5)
+    r = NeRFRenderer.from_conf(ConfigTree.from_dict(conf)).eval().cuda()
+    r.load_state_dict(src.state_dict())
+    net = H.build_net(H.make_scene_dict(), precision="bf16")
+    rays = H.rays_subset(1, 50)
+    with torch.no_grad():
+        out = r(net, rays.cuda(), want_weights=True)
+    assert (r.n_coarse, r.n_fine) == (128, 64)
+    assert out.coarse.weights.shape == (1, 50, 128) and out.fine.weights.shape == (1, 50, 192)
+    noise = H.make_noise(50, kc=128, kf=48, kfd=16)
+    r.noise_override = {k: v.cuda() for k, v in noise.items()}
+    with torch.no_grad():
+        res = r(net, rays.cuda())
+    ref = O.render(H.oracle_scene(H.make_scene_dict()), synth.mlp_state(1), synth.mlp_state(2), rays,
+                   O.RenderNoise(noise["coarse"], noise["fine_u"], noise["fine_jitter"], noise["depth"]), n_coarse=128, n_fine=64)
+    assert (res.fine.rgb.cpu() - ref["fine"]["rgb"]).abs().max() < 1e-2
+    assert (res.fine.depth.cpu() - ref["fine"]["depth"]).abs().max() < 1e-2

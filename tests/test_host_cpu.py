@@ -136,3 +136,28 @@ def test_sharded_render_two_ranks_gloo_matches_single():
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_SHARD_OK" in r.stdout
+
+
+def test_sched_step_follows_reference_schedule():
+    """nerf.py:324-344: sched = [iteration thresholds, n_coarse values, n_fine values]; the persistent buffers iter_idx /
+    last_sched carry the position through a checkpoint (forward re-reads the resolution from last_sched, nerf.py:271-273)."""
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    conf = {"n_coarse": 64, "n_fine": 32, "n_fine_depth": 16, "sched": [[2, 5], [96, 128], [48, 64]]}
+    r = NeRFRenderer.from_conf(ConfigTree.from_dict(conf))
+    seen = []
+    for _ in range(6):
+        r.sched_step()
+        seen.append((int(r.iter_idx), int(r.last_sched), r.n_coarse, r.n_fine))
+    assert seen == [(1, 0, 64, 32), (2, 1, 96, 48), (3, 1, 96, 48), (4, 1, 96, 48), (5, 2, 128, 64), (6, 2, 128, 64)]
+    r.sched_step(10)                                    # past the last threshold: nothing more to change
+    assert (int(r.last_sched), r.n_coarse, r.n_fine) == (2, 128, 64)
+    r2 = NeRFRenderer.from_conf(ConfigTree.from_dict(conf))
+    r2.load_state_dict(r.state_dict())
+    assert int(r2.iter_idx) == 16 and int(r2.last_sched) == 2 and r2.n_coarse == 64     # restored lazily, at the next forward
+    r3 = NeRFRenderer.from_conf(ConfigTree.from_dict(conf))
+    r3.sched_step(3)                                    # a multi-iteration step crosses one threshold
+    assert (int(r3.last_sched), r3.n_coarse, r3.n_fine) == (1, 96, 48)
+    none = NeRFRenderer.from_conf(ConfigTree.from_dict({"n_coarse": 64, "sched": []}))
+    none.sched_step()
+    assert int(none.iter_idx) == 0 and none.sched is None

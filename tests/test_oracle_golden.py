@@ -77,3 +77,36 @@ def test_render_matches_reference(golden):
                                            err_msg=f"{tag} {lvl} {k}")
         # both passes have non-trivial opacity, so the MLP output really reaches the pixels
         assert 0.3 < golden[f"{tag}_fine_weights"].sum(-1).mean() < 0.99
+
+
+# ---------------------------------------------------------------------------------- lindisp (nerf.py:121,153; DTU renders with it)
+def lindisp_case():
+    """Inputs of tests/golden/make_golden_lindisp.py rebuilt from the stored indices/bounds/noise."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_lindisp.npz"))
+    rays = synth.target_rays(128, 15.0, -10.0)[:, T(g["ray_idx"]).long()].clone()
+    rays[0, :, 6], rays[0, :, 7] = T(g["near"]), T(g["far"])
+    noise = {k: T(g[f"noise_{k}"]) for k in ("coarse", "fine_u", "fine_jitter", "depth")}
+    return g, rays, noise
+
+
+def test_lindisp_samplers_bit_exact():
+    g, rays, nz = lindisp_case()
+    r = rays.reshape(-1, 8)
+    assert torch.equal(O.sample_coarse(r, nz["coarse"], 64, lindisp=True), T(g["z_coarse"]))
+    w = T(g["coarse_weights"]).reshape(-1, 64)
+    assert torch.equal(O.sample_fine(r, w, nz["fine_u"], nz["fine_jitter"], 64, lindisp=True), T(g["z_fine"]))
+    assert torch.equal(O.sample_fine_depth(r, T(g["coarse_depth"]).reshape(-1), nz["depth"], 0.01), T(g["z_depth"]))
+    # the variant is really exercised: sample spacing grows along the ray (uniform in 1/z)
+    zc = g["z_coarse"]
+    assert ((zc[:, -1] - zc[:, -9]) > 2 * (zc[:, 8] - zc[:, 0])).all()
+
+
+def test_lindisp_render_matches_reference():
+    g, rays, nz = lindisp_case()
+    res = O.render(_scene(1), synth.mlp_state(1), synth.mlp_state(2), rays,
+                   O.RenderNoise(nz["coarse"], nz["fine_u"], nz["fine_jitter"], nz["depth"]), white_bkgd=False, lindisp=True)
+    for lvl in ("coarse", "fine"):
+        for k in ("rgb", "depth", "weights"):
+            np.testing.assert_allclose(res[lvl][k].numpy(), g[f"{lvl}_{k}"], atol=3e-5, rtol=1e-4, err_msg=f"{lvl} {k}")
+    assert 0.3 < g["fine_weights"].sum(-1).mean() < 0.99
