@@ -478,3 +478,24 @@ def test_scheduled_resolution_is_applied_at_forward(lib):
                    O.RenderNoise(noise["coarse"], noise["fine_u"], noise["fine_jitter"], noise["depth"]), n_coarse=128, n_fine=64)
     assert (res.fine.rgb.cpu() - ref["fine"]["rgb"]).abs().max() < 1e-2
     assert (res.fine.depth.cpu() - ref["fine"]["depth"]).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_camera_formats_match_reference_golden(lib, precision, tol):
+    """focal as a scalar / (SB,) / (SB, 2) / one (1, 2) row, principal point absent / scalar / (SB,) / (SB, 2): the drop-in's
+    set_cameras broadcasts per-object rows over the source views exactly as models.py:225-230 does (SB = 2 x 3 views)."""
+    from test_oracle_golden import CAMERA_CASES, camera_goldens
+    g = camera_goldens()
+    scene = H.make_scene_dict(num_objs=2)
+    net = H.build_net(scene, precision=precision)
+    xyz, dirs = T(g["xyz"]).cuda(), T(g["dirs"]).cuda()
+    for name in CAMERA_CASES:
+        c = T(g[name + "_c"]).cuda() if name + "_c" in g else None
+        net.set_cameras(scene["poses"].reshape(-1, 4, 4).cuda(), T(g[name + "_focal"]).cuda(), scene["image_wh"], c)
+        with torch.no_grad():
+            out = net(xyz, coarse=True, viewdirs=dirs)
+        ref = g[name]
+        err_rgb = np.abs(out[..., :3].cpu().numpy() - ref[..., :3]).max()
+        # sigma is unbounded (values up to ~10 here): bf16 operand rounding scales with it
+        err_sig = (np.abs(out[..., 3].cpu().numpy() - ref[..., 3]) / np.maximum(1.0, np.abs(ref[..., 3]))).max()
+        assert err_rgb < tol and err_sig < tol, (name, err_rgb, err_sig)

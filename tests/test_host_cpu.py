@@ -161,3 +161,28 @@ def test_sched_step_follows_reference_schedule():
     none = NeRFRenderer.from_conf(ConfigTree.from_dict({"n_coarse": 64, "sched": []}))
     none.sched_step()
     assert int(none.iter_idx) == 0 and none.sched is None
+
+
+def test_state_dict_is_checkpoint_compatible_with_reference():
+    """A checkpoint written by the reference's trainer loads with strict=True: same names, shapes and dtypes as the
+    unmodified reference's state_dict (manifest generated by tests/golden/make_golden_state_dict.py), same PE buffers."""
+    import json
+    from helpers import MODEL_CONF, RENDER_CONF
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.model import make_model
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_state_dict.json")))
+    net = make_model(ConfigTree.from_dict(MODEL_CONF))
+    sd = net.state_dict()
+    ours = {k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}
+    assert set(ours) == set(man["model"]), (sorted(set(ours) - set(man["model"]))[:5], sorted(set(man["model"]) - set(ours))[:5])
+    assert ours == man["model"]
+    assert sd["code._freqs"].flatten().tolist() == man["code._freqs"]
+    assert sd["code._phases"].flatten().tolist() == man["code._phases"]
+    assert sum(p.numel() for p in net.parameters()) == man["n_params"]
+    r = NeRFRenderer.from_conf(ConfigTree.from_dict(RENDER_CONF))
+    assert {k: [list(v.shape), str(v.dtype)] for k, v in r.state_dict().items()} == man["renderer"]
+    # a synthetic "reference checkpoint" with exactly the manifest's entries loads strictly
+    import torch
+    fake = {k: torch.zeros(shape, dtype=getattr(torch, dt.split(".")[1])) for k, (shape, dt) in man["model"].items()}
+    net.load_state_dict(fake, strict=True)

@@ -110,3 +110,22 @@ def test_lindisp_render_matches_reference():
         for k in ("rgb", "depth", "weights"):
             np.testing.assert_allclose(res[lvl][k].numpy(), g[f"{lvl}_{k}"], atol=3e-5, rtol=1e-4, err_msg=f"{lvl} {k}")
     assert 0.3 < g["fine_weights"].sum(-1).mean() < 0.99
+
+
+# ---------------------------------------------------------------------------------- intrinsics formats (models.py:124-148, 225-230)
+CAMERA_CASES = ("scalar_focal_scalar_c", "per_object_focal_vec_c", "per_object_fxfy_cxcy", "single_row_fxfy_no_c")
+
+
+def camera_goldens():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cameras.npz"))
+
+
+def test_camera_formats_match_reference():
+    g = camera_goldens()
+    s = synth.scene_config1(seed=5, num_views=3, C=512, size=128, feat=16, num_objs=2)
+    for name in CAMERA_CASES:
+        c = T(g[name + "_c"]) if name + "_c" in g else None
+        sc = O.encode_cameras(s["latent"], s["poses"], T(g[name + "_focal"]), s["image_wh"], c=c)
+        out = O.field_forward(sc, synth.mlp_state(1), T(g["xyz"]), T(g["dirs"]))
+        np.testing.assert_allclose(out.numpy(), g[name], atol=2e-5, rtol=1e-5, err_msg=name)
