@@ -499,3 +499,40 @@ def test_camera_formats_match_reference_golden(lib, precision, tol):
         # sigma is unbounded (values up to ~10 here): bf16 operand rounding scales with it
         err_sig = (np.abs(out[..., 3].cpu().numpy() - ref[..., 3]) / np.maximum(1.0, np.abs(ref[..., 3]))).max()
         assert err_rgb < tol and err_sig < tol, (name, err_rgb, err_sig)
+
+
+def test_render_without_fine_network_uses_coarse_network(lib):
+    """eval/eval.py:140 sets ``net.mlp_fine = None`` for coarse-only checkpoints; the fine pass then runs the coarse network
+    (models.py:291) -- on the single-call path (null mlp_fine in pnr_render_args) and on the staged path alike."""
+    scene = H.make_scene_dict()
+    net = H.build_net(scene, precision="bf16")
+    net.mlp_fine = None
+    rays, noise = H.rays_subset(1, 100), H.make_noise(100)
+    res = _render_cuda(net, rays, noise)
+    ref = O.render(H.oracle_scene(scene), synth.mlp_state(1), None, rays,
+                   O.RenderNoise(noise["coarse"], noise["fine_u"], noise["fine_jitter"], noise["depth"]))
+    for lvl in ("coarse", "fine"):
+        assert (res[lvl].rgb.cpu() - ref[lvl]["rgb"]).abs().max() < 1e-2
+        assert (res[lvl].depth.cpu() - ref[lvl]["depth"]).abs().max() < 1e-2
+    two = O.render(H.oracle_scene(scene), synth.mlp_state(1), synth.mlp_state(2), rays,
+                   O.RenderNoise(noise["coarse"], noise["fine_u"], noise["fine_jitter"], noise["depth"]))
+    assert (two["fine"]["rgb"] - ref["fine"]["rgb"]).abs().max() > 5e-2      # the fine network would have given another image
+    net.fused_render_ready = lambda: False
+    staged = _render_cuda(net, rays, noise)
+    assert torch.equal(staged.fine.rgb, res.fine.rgb) and torch.equal(staged.fine.depth, res.fine.depth)
+
+
+def test_render_wrapper_dict_output(lib):
+    """nerf.py:28-48: without simple_output the bound module returns plain dicts (what DataParallel can gather)."""
+    net = H.build_net(H.make_scene_dict(), precision="bf16")
+    r = _renderer()
+    wrapped = r.bind_parallel(net, None, simple_output=False).eval()
+    rays = H.rays_subset(1, 40).cuda()
+    with torch.no_grad():
+        out = wrapped(rays, want_weights=True)
+        plain = wrapped(rays)
+    assert type(out) is dict and set(out) == {"coarse", "fine"} and type(out["fine"]) is dict
+    assert set(out["fine"]) == {"rgb", "depth", "weights"} and set(plain["fine"]) == {"rgb", "depth"}
+    assert out["coarse"]["weights"].shape == (1, 40, 64) and out["fine"]["weights"].shape == (1, 40, 96)
+    w = out["fine"]["weights"]
+    assert (w >= 0).all() and (w.sum(-1) <= 1 + 1e-5).all()
