@@ -359,8 +359,12 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         int st = fi < G * s_pre ? fi % s_pre : fi - (G - 1) * s_pre;   // G passes over the pre stages, one over the post stages
         for (; fi < n_flat; fi += kProducers) {
           mbar_wait_cluster(bar(B_W_EMPTY + slot), par);
+#ifdef PNR_DIAG_NOWEIGHTS   // timing diagnostic only (wrong results): the weight slot is declared full without loading anything
+          if (crank == 0) mbar_arrive(bar(B_W_FULL + slot));
+#else
           if (crank == 0) mbar_arrive_expect_tx(bar(B_W_FULL + slot), 2 * kStageBytes);
           tma_load_2d_2sm(sbase + Smem::w + slot * kStageBytes, &wmap, 0, (st * 2 + (int)crank) * kStageRows, bar(B_W_FULL + slot));
+#endif
           slot += kProducers;
           if (slot >= kStages) { slot -= kStages; par ^= 1; }
           // next stage id without a division: inside the pre passes the id wraps at s_pre, after them it just continues
@@ -507,8 +511,13 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
+#ifdef PNR_DIAG_NOEPI   // timing diagnostic only (wrong results): no rows were stored, so no bytes are expected
+          if (crank == 0) mbar_arrive(bar(B_RDY + kc));
+          mbar_arrive_cluster_relaxed(land_bar(kc));
+#else
           if (crank == 0) { mbar_arrive(bar(B_RDY + kc)); mbar_arrive_expect_tx_cluster(land_bar(kc), kRemoteBytes); }
           else mbar_arrive_expect_tx_cluster(land_bar(kc), kRemoteBytes);      // = the leader's chunk barrier
+#endif
         }
       } else {
         fence_proxy_async_cluster();               // waits until this warp's local AND remote rows are performed
@@ -523,6 +532,10 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     auto convert_unit = [&](uint32_t tcol, int kc, float bias) {
       const uint32_t loc = sbase + Smem::ring + kc * kChunkBytes;
       const uint32_t rem = mapa_u32(loc, peer);
+#ifdef PNR_DIAG_NOEPI   // timing diagnostic only (wrong results): the regular epilogues cost nothing but their barrier traffic
+      (void)loc; (void)rem; (void)tcol; (void)bias;
+      return;
+#endif
       uint32_t v[kNCol / 2], u[kNCol / 2];
       tmem_ld_nowait<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);     // both halves in flight at once
       tmem_ld_nowait<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), u);
@@ -599,8 +612,12 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           for (int c = 0; c < kNCol / 2; ++c)
             v[c] = (hs * (kNCol / 2) + c < NLIVE) ? __float_as_uint(__ldcg(src + (size_t)c * kHidden)) : 0u;
           tmem_st<kNCol / 2>(tlane + mt * 128 + t * kNCol + hs * (kNCol / 2), v);
+#ifndef PNR_DIAG_NOEPI
           if (half == 0) store_transposed<kNCol / 2, true, false>(mapa_u32(loc, peer), v, 0.f, lane, qd * 32, hs * (kNCol / 2), ASYNC ? land_bar(kc) : 0u);
           else store_transposed<kNCol / 2, false, false>(loc, v, 0.f, lane, qd * 32, hs * (kNCol / 2));
+#else
+          (void)loc;
+#endif
         }
         publish(kc);
       }

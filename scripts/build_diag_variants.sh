@@ -1,0 +1,22 @@
+#!/bin/bash
+# Timing-diagnostic builds of the pair kernel (WRONG RESULTS, timing only): each variant removes one cost so that the step time
+# without it bounds what a redesign of that part could gain.  Built here (nvcc needs ~2 min per variant), measured with
+# scripts/gpu_diag_bounds.sh on the GPU box.  The product library is never replaced in the repository.
+cd "$(dirname "$0")/.."
+CS=pixel-nerf-yolo_b200/csrc
+D=$CS/build/diag
+mkdir -p $D
+python -m pixel_nerf_yolo_b200.build > /dev/null || exit 1      # product objects (all other translation units)
+build_one() {   # name, flags...
+  local name=$1; shift
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c $CS/mlp_umma_pair.cu -o $D/pair_$name.o 2> $D/pair_$name.log || { echo "compile $name failed"; return 1; }
+  objs=$(ls $CS/build/*.o | grep -v mlp_umma_pair.o)
+  nvcc -shared -o $D/lib_$name.so $objs $D/pair_$name.o -gencode arch=compute_100a,code=sm_100a && echo "built $D/lib_$name.so"
+}
+build_one noweights -DPNR_DIAG_NOWEIGHTS &
+build_one noepi -DPNR_DIAG_NOEPI &
+build_one nogather -DPNR_DIAG_NOGATHER &
+build_one noweights_noepi -DPNR_DIAG_NOWEIGHTS -DPNR_DIAG_NOEPI &
+build_one none3 -DPNR_DIAG_NOWEIGHTS -DPNR_DIAG_NOEPI -DPNR_DIAG_NOGATHER &
+wait
+ls -la $D/*.so
