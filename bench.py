@@ -307,12 +307,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=None,
-                    help="rays in the bounded CPU sample (default 2048 for cpu_baseline, 512 per step for --impl reference)")
+                    help="rays in the bounded CPU sample (default 4096 for cpu_baseline = 10-15 s of CPU work, 512 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.cpu_rays is None:
-        args.cpu_rays = 2048 if args.impl == "ours" else 512
+        args.cpu_rays = 4096 if args.impl == "ours" else 512
     if args.impl == "reference":
         run_reference(args)
     else:
