@@ -252,12 +252,17 @@ def oracle_inputs(scene, latent_cpu):
     return O, sc, synth.mlp_state(1), synth.mlp_state(2)
 
 
-def time_oracle(O, sc, mc, mf, rays, seed=0):
-    B = rays.shape[1]
-    noise = O.RenderNoise.draw(B, KC, KF, KFD, generator=torch.Generator().manual_seed(seed))
-    t0 = time.perf_counter()
-    O.render(sc, mc, mf, rays, noise, n_coarse=KC, n_fine=KF, n_fine_depth=KFD, white_bkgd=True)
-    return time.perf_counter() - t0
+def time_oracle(O, sc, mc, mf, rays, seed=0, chunk=1024):
+    """Wall time of the oracle render of `rays`, in ray chunks of `chunk` (the reference chunks its model calls too,
+    nerf.py:209-222; rays are independent, so the arithmetic per ray is the same) to bound host memory."""
+    total = 0.0
+    for s in range(0, rays.shape[1], chunk):
+        r = rays[:, s:s + chunk]
+        noise = O.RenderNoise.draw(r.shape[1], KC, KF, KFD, generator=torch.Generator().manual_seed(seed + s))
+        t0 = time.perf_counter()
+        O.render(sc, mc, mf, r, noise, n_coarse=KC, n_fine=KF, n_fine_depth=KFD, white_bkgd=True)
+        total += time.perf_counter() - t0
+    return total
 
 
 def cpu_baseline(scene, net, sample_rays):
