@@ -130,9 +130,13 @@ def test_shard_bounds_cover_and_align():
 
 def test_sharded_render_two_ranks_gloo_matches_single():
     """world_size-2 gloo run of ShardedRenderer: gathered output == the unsharded render, bit for bit."""
+    import socket
     script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    with socket.socket() as sk:                      # a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29611", script],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), script],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_SHARD_OK" in r.stdout
