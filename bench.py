@@ -3,17 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One step = one full target image (16 384 rays, 64 coarse + 96 fine samples per ray, 3 source views,
-resnet34-sized 512-channel feature maps, random-init weights) through NeRFRenderer.forward.
-`value` is device-timed with the rays already in HBM; `e2e` is the same render through the public API
-(`renderer.bind_parallel(net, ..., simple_output=True)(rays)`) with the rays in pinned host memory and the
-pixels copied back to the host inside the timed region.  Under torchrun (N>1) every rank renders its own
-target view (weak scaling: N views for N GPUs) and the packed (rgb, depth) outputs are all-gathered once
-per step with NCCL inside the timed region; the time is the max over ranks.
+One step = ONE full target image (16 384 rays, 64 coarse + 96 fine samples per ray, 3 source views, resnet34-sized
+512-channel feature maps, random-init weights) through NeRFRenderer.forward.
 
-`--impl reference` times the reference's CPU implementation of the same path on the host cores.  The
-reference is pure Python/PyTorch and cannot travel to the GPU box, so this arm runs the oracle port
-(oracle/pixelnerf_oracle.py, pinned to the reference's outputs by tests/test_oracle_golden.py).
+* N = 1: `value` is device-timed with the rays already in HBM; `e2e` is the same render through the public API
+  (`renderer.bind_parallel(net, ..., simple_output=True)(rays)`) with the rays in pinned host memory and the pixels copied
+  back to the host inside the timed region.
+* N > 1 (torchrun): STRONG scaling -- the SAME image is split into ray slices by the product's `dist.ShardedRenderer`
+  (what the reference does with DataParallel(dim=1), src/render/nerf.py:373-377): every rank renders ceil(16384/N) rays and
+  the packed (rgb, depth) rows are all-gathered once per step with NCCL, inside both timed regions; time = max over ranks.
+  Before timing every rank checks that the gathered image equals its own full single-GPU render bit for bit
+  (`sharded_equals_single_gpu` in the line).
+
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, copied from /root/reference by baseline/make_ref.py) on the
+host cores: same scene tensors, same weights, same workload, a bounded ray sample per step.  If baseline/_ref is missing it
+falls back to the oracle port and says so (`kind: "port"`).
 """
 import argparse
 import json
@@ -31,10 +35,31 @@ sys.path.insert(0, ROOT)
 SIZE, NS, KC, KF, KFD = 128, 3, 64, 32, 16
 H, D_IN, C_LAT, D_OUT = 512, 42, 512, 4
 POINTS_PER_RAY = KC + (KC + KF)                                    # 160
-# MACs per (point, view) row and per point, FLOPs = 2 * MACs
-FLOP_PER_POINT = 2 * (NS * (D_IN * H + 3 * (C_LAT * H + 2 * H * H)) + 2 * 2 * H * H + H * D_OUT)
-FLOP_PER_RAY = FLOP_PER_POINT * POINTS_PER_RAY                     # 2.6218 GFLOP
+METRIC = "rays/sec (samples/sec) 3-view render at 1/2/4/8 B200 vs host-CPU ref"
 WORKLOAD = "config2: 3-view 128x128 full-image render, 16384 rays, 64 coarse + 32 fine (16 importance + 16 depth), bf16 ResnetFC"
+MODEL_CONF = {
+    "use_encoder": True, "use_global_encoder": False, "use_xyz": True, "use_code": True,
+    "code": {"num_freqs": 6, "freq_factor": 1.5, "include_input": True}, "use_viewdirs": True, "use_code_viewdirs": False,
+    "mlp_coarse": {"type": "resnet", "n_blocks": 5, "d_hidden": 512, "d_out": 4, "combine_layer": 3, "combine_type": "average"},
+    "mlp_fine": {"type": "resnet", "n_blocks": 5, "d_hidden": 512, "d_out": 4, "combine_layer": 3, "combine_type": "average"},
+    "encoder": {"backbone": "resnet34", "pretrained": False, "num_layers": 4, "index_padding": "zeros"},
+}
+
+
+def flop_per_ray(ns=NS, c=C_LAT, kc=KC, kf=KF, h=H, d_in=D_IN, d_out=D_OUT):
+    """MACs per (point, view) row and per point, FLOPs = 2 * MACs."""
+    per_pt = 2 * (ns * (d_in * h + 3 * (c * h + 2 * h * h)) + 2 * 2 * h * h + h * d_out)
+    return per_pt * (kc + kc + kf)
+
+
+FLOP_PER_RAY = flop_per_ray()                                       # 2.6218 GFLOP
+
+
+def bench_config(world):
+    """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "rays_per_image": SIZE * SIZE, "source_views": NS, "samples_per_ray": POINTS_PER_RAY,
+            "feature_maps": "3x512x64x64 (random-init resnet34 on synthetic images, divided by its std)",
+            "scene": "seeded: torch.manual_seed(0) network, synth.scene_config1(0) cameras, U[-1,1] images, target pose_spherical(15,-10,1.3)"}
 
 
 def peaks():
@@ -47,13 +72,14 @@ def peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the field kernel per launch (mean of the coarse and the fine launch
-    of this workload), copied from the committed `ncu --set full` capture; None if no capture is recorded."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the field kernel per launch, CITED from the committed `ncu --set full`
+    capture named in profiles/traffic.json (not a measurement of this run); None if no capture is recorded."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p))["field_pair_kernel"]["dram_bytes_per_launch"]
+        d = json.load(open(p))["field_pair_kernel"]
+        return d["dram_bytes_per_launch"], d.get("capture", "profiles/traffic.json")
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -93,36 +119,267 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_inputs(rank, device):
-    """Scene (3 source views through the random-init resnet34 encoder), weights and this rank's target view."""
+# ---------------------------------------------------------------------------------------------------------------------
+# Scene shared by every arm: the SAME tensors reach the GPU path, the reference on the CPU and the reference on the GPU.
+def scene_inputs():
+    import pixel_nerf_yolo_b200.synth as synth
+    scene = synth.scene_config1(seed=0, num_views=NS, C=C_LAT, size=SIZE)
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(1, NS, 3, SIZE, SIZE, generator=g) * 2 - 1
+    rays = synth.target_rays(SIZE, theta=15.0, phi=-10.0)                       # (1, 16384, 8), host
+    return scene, images, rays
+
+
+def build_ours(device):
+    """Drop-in network + renderer on `device`: random-init resnet34 trunk (torch.manual_seed(0)), synthetic exercised MLPs,
+    the 3 source views encoded, latent normalised to O(1)."""
     import pixel_nerf_yolo_b200.synth as synth
     from pixel_nerf_yolo_b200.conf import ConfigTree
     from pixel_nerf_yolo_b200.model import make_model
     from pixel_nerf_yolo_b200.render import NeRFRenderer
-    conf = {
-        "use_encoder": True, "use_global_encoder": False, "use_xyz": True, "use_code": True,
-        "code": {"num_freqs": 6, "freq_factor": 1.5, "include_input": True}, "use_viewdirs": True, "use_code_viewdirs": False,
-        "mlp_coarse": {"type": "resnet", "n_blocks": 5, "d_hidden": 512, "d_out": 4, "combine_layer": 3, "combine_type": "average"},
-        "mlp_fine": {"type": "resnet", "n_blocks": 5, "d_hidden": 512, "d_out": 4, "combine_layer": 3, "combine_type": "average"},
-        "encoder": {"backbone": "resnet34", "pretrained": False, "num_layers": 4, "index_padding": "zeros"},
-    }
+    scene, images, rays = scene_inputs()
     torch.manual_seed(0)
-    net = make_model(ConfigTree.from_dict(conf)).eval()
+    net = make_model(ConfigTree.from_dict(MODEL_CONF)).eval()
     net.mlp_coarse.load_state_dict(synth.mlp_state(1))
     net.mlp_fine.load_state_dict(synth.mlp_state(2))
+    state = {k: v.clone() for k, v in net.state_dict().items()}                 # handed to the reference arms
     net = net.to(device)
-    scene = synth.scene_config1(seed=0, num_views=NS, C=C_LAT, size=SIZE)
-    g = torch.Generator().manual_seed(0)
-    images = (torch.rand(1, NS, 3, SIZE, SIZE, generator=g) * 2 - 1).to(device)
+    net.requires_grad_(False)
     with torch.no_grad():
-        net.encode(images, scene["poses"].to(device), scene["focal"].to(device))         # real resnet34 trunk, random init
+        net.encode(images.to(device), scene["poses"].to(device), scene["focal"].to(device))
         lat = net.encoder.latent
-        net.encoder.set_latent(lat / lat.std())                                          # O(1) features (SURVEY.md section 0)
+        net.encoder.set_latent(lat / lat.std())
     renderer = NeRFRenderer(KC, KF, KFD, depth_std=0.01, white_bkgd=True, eval_batch_size=50000).eval().to(device)
-    rays = synth.target_rays(SIZE, theta=15.0 + 15.0 * rank, phi=-10.0)                  # (1, 16384, 8), host
-    return net, renderer, rays, scene
+    return net, renderer, rays, scene, images, state
 
 
+def build_reference(device, state=None):
+    """The unmodified reference's network + renderer (baseline/_ref) with the same weights, scene and normalisation."""
+    from baseline.ref_shims import load_reference
+    R = load_reference()
+    if R is None:
+        return None
+    import pixel_nerf_yolo_b200.synth as synth
+    scene, images, rays = scene_inputs()
+    if state is None:
+        from pixel_nerf_yolo_b200.conf import ConfigTree
+        from pixel_nerf_yolo_b200.model import make_model
+        torch.manual_seed(0)
+        ours = make_model(ConfigTree.from_dict(MODEL_CONF))
+        ours.mlp_coarse.load_state_dict(synth.mlp_state(1))
+        ours.mlp_fine.load_state_dict(synth.mlp_state(2))
+        state = ours.state_dict()
+    conf = R.Conf({"model": MODEL_CONF, "renderer": {"n_coarse": KC, "n_fine": KF, "n_fine_depth": KFD, "depth_std": 0.01,
+                                                    "sched": [], "white_bkgd": True}})
+    import contextlib
+    import warnings
+    with warnings.catch_warnings(), contextlib.redirect_stdout(sys.stderr):      # the reference prints while it builds
+        warnings.simplefilter("ignore")
+        net = R.make_model(conf["model"]).eval()
+        net.load_state_dict(state, strict=True)                                 # same names/shapes as the drop-in's
+        net = net.to(device)
+        with torch.no_grad():
+            net.encode(images.to(device), scene["poses"].to(device), scene["focal"].to(device))
+            net.encoder.latent = net.encoder.latent / net.encoder.latent.std()
+        renderer = R.NeRFRenderer.from_conf(conf["renderer"], eval_batch_size=50000).to(device)
+        render_par = renderer.bind_parallel(net, None, simple_output=True).eval()
+    return render_par, rays, R
+
+
+def time_reference_cpu(render_par, rays, steps, warmup):
+    """Wall time of `steps` reference renders of `rays` on the host cores."""
+    with torch.no_grad():
+        for _ in range(warmup):
+            render_par(rays[:, :64])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            render_par(rays)
+        return time.perf_counter() - t0
+
+
+def sample_rays(rays, n):
+    stride = max(1, rays.shape[1] // n)
+    return rays[:, ::stride][:, :n].contiguous(), stride
+
+
+def cpu_baseline(state, n_rays):
+    """The reference itself (kind "reference") on all host cores, bounded sample of the same image; oracle port if absent."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    built = build_reference(torch.device("cpu"), state)
+    if built is not None:
+        render_par, rays, R = built
+        sub, stride = sample_rays(rays, n_rays)
+        dt = time_reference_cpu(render_par, sub, 1, 1)
+        return {"value": sub.shape[1] / dt, "unit": "rays/s", "cores": cores, "kind": "reference",
+                "sample": f"{sub.shape[1]} rays of the same 128x128 view (every {stride}th ray), {dt:.1f} s, unmodified reference "
+                          f"(baseline/_ref) NeRFRenderer.forward, torch {torch.__version__} fp32, {cores} threads"}
+    return cpu_baseline_port(n_rays)
+
+
+def cpu_baseline_port(n_rays):
+    import pixel_nerf_yolo_b200.synth as synth
+    from oracle import pixelnerf_oracle as O
+    cores = os.cpu_count() or 1
+    scene = synth.scene_config1(seed=0, num_views=NS, C=C_LAT, size=SIZE)
+    sc = O.encode_cameras(scene["latent"], scene["poses"], scene["focal"], scene["image_wh"])
+    mc, mf = synth.mlp_state(1), synth.mlp_state(2)
+    sub, stride = sample_rays(synth.target_rays(SIZE), n_rays)
+    total = 0.0
+    for s in range(0, sub.shape[1], 1024):
+        r = sub[:, s:s + 1024]
+        noise = O.RenderNoise.draw(r.shape[1], KC, KF, KFD, generator=torch.Generator().manual_seed(s))
+        t0 = time.perf_counter()
+        O.render(sc, mc, mf, r, noise, n_coarse=KC, n_fine=KF, n_fine_depth=KFD, white_bkgd=True)
+        total += time.perf_counter() - t0
+    return {"value": sub.shape[1] / total, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{sub.shape[1]} rays (every {stride}th ray), {total:.1f} s, oracle port (baseline/_ref missing), {cores} threads"}
+
+
+def gpu_eager_baseline(state, device):
+    """'the bar is the reference's eager fp32 path on the same B200' -- the unmodified reference modules
+    on cuda:0, fp32, TF32 off, 50 000-point chunks (eval/eval.py:264-281), whole 16 384-ray image, CUDA events."""
+    built = build_reference(device, state)
+    if built is None:
+        return None
+    render_par, rays, R = built
+    tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        rays_dev = rays.to(device)
+        with torch.no_grad():
+            render_par(rays_dev[:, :2048])
+            torch.cuda.synchronize()
+            ms = []
+            for _ in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                render_par(rays_dev)
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+    best = min(ms)
+    return {"value": rays.shape[1] / (best * 1e-3), "unit": "rays/s", "ms_per_image": best, "kind": "reference",
+            "what": "unmodified reference (baseline/_ref) NeRFRenderer.forward on cuda:0, eager fp32 (allow_tf32=False), "
+                    "ray_batch_size 50000, same scene/weights/workload, best of 2 after a 2048-ray warm-up"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def config4_strong(device, world, rank):
+    """BASELINE config 4 as extra keys: 640x640 target view (409 600 rays), 3 x 1792 x 80 x 80 maps (synthetic, YOLO-backbone
+    sized), rays sharded over the ranks by dist.ShardedRenderer; 1 warm-up + 2 timed steps."""
+    import copy
+    import torch.distributed as dist
+    import pixel_nerf_yolo_b200.synth as synth
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.dist import ShardedRenderer
+    from pixel_nerf_yolo_b200.model import make_model
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    C4, S4, F4 = 1792, 640, 80
+    conf = copy.deepcopy(MODEL_CONF)
+    conf["encoder"] = {"backbone": "custom", "pretrained": False, "num_layers": 4, "index_padding": "zeros"}
+    scene = synth.scene_config1(seed=5, num_views=NS, C=C4, size=S4, feat=F4)
+    net = make_model(ConfigTree.from_dict(conf)).eval()
+    net.mlp_coarse.load_state_dict(synth.mlp_state(1, d_latent=C4))
+    net.mlp_fine.load_state_dict(synth.mlp_state(2, d_latent=C4))
+    net = net.to(device)
+    net.requires_grad_(False)
+    net.num_objs, net.num_views_per_obj = 1, NS
+    net.encoder.set_latent(scene["latent"].to(device))
+    net.set_cameras(scene["poses"].reshape(-1, 4, 4).to(device), scene["focal"].to(device), scene["image_wh"])
+    renderer = NeRFRenderer(KC, KF, KFD, depth_std=0.01, white_bkgd=True).eval().to(device)
+    rays = synth.target_rays(S4).to(device)
+    if world > 1:
+        fn = ShardedRenderer.for_renderer(renderer, net)
+    else:
+        wrapped = renderer.bind_parallel(net, None, simple_output=True).eval()
+        fn = wrapped
+    steps, ms = 2, 0.0
+    with torch.no_grad():
+        fn(rays)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(rays)
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    n = rays.shape[1]
+    fl = flop_per_ray(c=C4) * n
+    del net, renderer, rays
+    torch.cuda.empty_cache()
+    return {"workload": "config4: 640x640 target view (409600 rays), 3 views, synthetic 3x1792x80x80 maps, 64+32 samples, "
+                        f"rays sharded over {world} GPU(s) (strong scaling)", "steps": steps, "ms_per_step": ms,
+            "rays_per_s": n / (ms * 1e-3), "algorithmic_tflops": fl / (ms * 1e-3) / 1e12,
+            "note": "algorithmic FLOPs count the 1792-wide lin_z the reference executes; this path gathers lin_z pre-projections "
+                    "(PNR_SCENE_PROJECTED) and executes the C=512-equivalent FLOPs, so this is not a roofline fraction",
+            "executed_tflops": flop_per_ray(c=512) * n / (ms * 1e-3) / 1e12}
+
+
+def train_step_block(device):
+    """BASELINE config 3 (PixelNerfTrainer.calc_losses + loss.backward(), train/trainlib/PixelNerfTrainer.py:133-157):
+    4 objects x 128 rays, 3 source views, forward + backward of the render (encoder trunk excluded), median of 3."""
+    import numpy as np
+    import pixel_nerf_yolo_b200.synth as synth
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.model import make_model
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    scene = synth.scene_config1(seed=5, num_views=NS, C=C_LAT, size=SIZE, feat=64, num_objs=4)
+    net = make_model(ConfigTree.from_dict(MODEL_CONF))
+    net.mlp_coarse.load_state_dict(synth.mlp_state(1))
+    net.mlp_fine.load_state_dict(synth.mlp_state(2))
+    net = net.to(device).train()
+    net.num_objs, net.num_views_per_obj = 4, NS
+    lat = scene["latent"].to(device).clone().requires_grad_(True)
+    net.encoder.set_latent(lat)
+    net.set_cameras(scene["poses"].reshape(-1, 4, 4).to(device), scene["focal"].to(device), scene["image_wh"])
+    out = {}
+    allr = torch.cat([synth.target_rays(SIZE, 15.0 + 20 * s, -10.0) for s in range(4)])
+    pick = torch.from_numpy(np.random.default_rng(1).choice(SIZE * SIZE, 128, replace=False)).long()
+    rays = allr[:, pick].contiguous().to(device)
+    gt = torch.rand(4, 128, 3, device=device)
+    params = [p for p in list(net.mlp_coarse.parameters()) + list(net.mlp_fine.parameters())]
+    r = NeRFRenderer(KC, KF, KFD, white_bkgd=True).train().to(device)
+    for prec in getattr(net, "TRAIN_PRECISIONS", ("tf32",)):
+        net.train_precision = prec
+
+        def step():
+            for p in params:
+                p.grad = None
+            lat.grad = None
+            res = r(net, rays)
+            loss = ((res.coarse.rgb - gt) ** 2).mean() + ((res.fine.rgb - gt) ** 2).mean()
+            loss.backward()
+        step()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        med = sorted(ms)[1]
+        out[prec] = {"ms_fwd_bwd": med, "rays_per_s": 512 / (med * 1e-3),
+                     "algorithmic_tflops": 3 * FLOP_PER_RAY * 512 / (med * 1e-3) / 1e12}
+    best = min(out, key=lambda k: out[k]["ms_fwd_bwd"])
+    return {"workload": "config3: train step, 4 objects x 128 rays, 3 views, 64+32 samples, forward + backward (MLP, gather, composite)",
+            "precision": best, **out[best], "all": out,
+            "flops": "3 x forward algorithmic FLOPs (forward + dgrad + wgrad)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -134,18 +391,42 @@ def run_ours(args):
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    from pixel_nerf_yolo_b200.dist import all_gather_rows
-    net, renderer, rays_host, scene = build_inputs(rank, device)
+    from pixel_nerf_yolo_b200.dist import ShardedRenderer, shard_bounds
+    net, renderer, rays_host, scene, images, state = build_ours(device)
     render_par = renderer.bind_parallel(net, None, simple_output=True).eval()
+    sharded = ShardedRenderer.for_renderer(renderer, net) if world > 1 else None
     rays_dev = rays_host.to(device)
     rays_pinned = rays_host.pin_memory()
     n_rays = rays_host.shape[1]
     out_pinned = torch.empty(n_rays, 4).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)                      # > 126 MB L2
-    bounds = [(i * n_rays, (i + 1) * n_rays) for i in range(world)]
+    bounds = shard_bounds(n_rays, world)
+    my_rays = bounds[rank][1] - bounds[rank][0]
 
-    # time the dominant kernel (fused field kernel) live, on the launching stream: the single-call render records CUDA events
-    # around its two field-kernel launches (pnr_render_args.field_events)
+    def render_full(r):
+        """One image through the public API: N = 1 the bound render module, N > 1 the sharded renderer (NCCL inside)."""
+        if world > 1:
+            rgb, depth = sharded(r)
+        else:
+            rgb, depth = render_par(r)
+        return torch.cat((rgb[0], depth[0].unsqueeze(-1)), dim=-1)                        # (B, 4) = 16 B/ray
+
+    # ---- parity of the sharded path, on this very workload, before anything is timed
+    parity = None
+    with torch.no_grad():
+        if world > 1:
+            torch.manual_seed(1234)
+            got = render_full(rays_dev)
+            torch.manual_seed(1234)
+            rgb, depth = render_par(rays_dev)                                              # this rank's own full render
+            ref = torch.cat((rgb[0], depth[0].unsqueeze(-1)), dim=-1)
+            ok = torch.tensor([1 if torch.equal(got, ref) else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            parity = bool(ok.item())
+            assert parity, "sharded render differs from the single-GPU render of the same seed"
+
+    # the dominant kernel is timed live on the launching stream: the single-call render records CUDA events around its two
+    # field-kernel launches (pnr_render_args.field_events)
     field_ms = []
 
     def arm_field_events():
@@ -154,18 +435,14 @@ def run_ours(args):
         field_ms.append((evs[0], evs[1]))
         field_ms.append((evs[2], evs[3]))
 
-    def step_device():
-        arm_field_events()
-        rgb, depth = render_par(rays_dev)
-        packed = torch.cat((rgb[0], depth[0].unsqueeze(-1)), dim=-1)                      # (B, 4) = 16 B/ray
-        if world > 1:
-            packed = all_gather_rows(packed, bounds)                                     # the path's one collective
-        return packed
+    def step_device(events=True):
+        if events:
+            arm_field_events()
+        return render_full(rays_dev)
 
     def step_e2e():
         r = rays_pinned.to(device, non_blocking=True)
-        rgb, depth = render_par(r)
-        packed = torch.cat((rgb[0], depth[0].unsqueeze(-1)), dim=-1)
+        packed = render_full(r)
         out_pinned.copy_(packed, non_blocking=True)
         return packed
 
@@ -187,23 +464,31 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    with torch.no_grad():
+    live_events = world == 1            # N > 1: the timed loops run with automatic slicing (no event hooks); the kernel is
+    with torch.no_grad():               # timed in a separate pass below
         for _ in range(args.warmup):
-            step_device()
+            step_device(live_events)
+            renderer.field_events = None
             step_e2e()
         field_ms.clear()
         sampler = ClockSampler(local)
         sync_all()
         if rank == 0:
             sampler.start()
-        ms_dev = timed_loop(step_device, args.steps)
+        ms_dev = timed_loop(lambda: step_device(live_events), args.steps)
         sync_all()
-        field_pairs = list(field_ms)
         renderer.field_events = None
         launches = renderer.last_launches
         ms_e2e = timed_loop(step_e2e, args.steps)
         sync_all()
         clocks = sampler.stop() if rank == 0 else None
+        roofline_pass = "live, inside the timed region"
+        if not live_events:
+            timed_loop(lambda: step_device(True), args.steps)
+            renderer.field_events = None
+            sync_all()
+            roofline_pass = f"separate {args.steps}-step pass after the timed region (event hooks disable the ray slicing of the timed path)"
+        field_pairs = list(field_ms)
     t = torch.tensor([ms_dev, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -211,95 +496,85 @@ def run_ours(args):
     field_total_ms = sum(a.elapsed_time(b) for a, b in field_pairs)
     n_field = len(field_pairs)
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(scene, net, sample_rays=args.cpu_rays)
+    extra = {}
+    if not args.no_extras:
+        extra["config4"] = config4_strong(device, world, rank)
+    cpu = eager = train = None
+    if rank == 0 and world == 1:
+        if not args.no_extras:
+            train = train_step_block(device)
+            eager = gpu_eager_baseline(state, device)
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(state, args.cpu_rays)
     if rank == 0:
         pk = peaks()
-        total_rays = world * n_rays * args.steps
-        flop_launch = FLOP_PER_RAY * n_rays * args.steps / max(n_field, 1)               # algorithmic FLOPs per field launch
+        total_rays = n_rays * args.steps                                                  # ONE image per step, whatever N
+        flop_launch = FLOP_PER_RAY * my_rays * args.steps / max(n_field, 1)               # algorithmic FLOPs per field launch (rank 0)
         achieved = (flop_launch / (field_total_ms / max(n_field, 1) * 1e-3)) / 1e12 if n_field else None
+        traffic, capture = ncu_traffic()
+        cfg = bench_config(world)
         line = {
-            "metric": "rays/sec (samples/sec) 3-view render at 1/2/4/8 B200 vs host-CPU ref", "value": total_rays / (ms_dev * 1e-3),
+            "metric": METRIC, "value": total_rays / (ms_dev * 1e-3),
             "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "samples_per_sec": total_rays * POINTS_PER_RAY / (ms_dev * 1e-3),
-            "config": {"workload": WORKLOAD, "rays_per_gpu": n_rays, "source_views": NS, "samples_per_ray": POINTS_PER_RAY,
-                       "feature_maps": "3x512x64x64 bf16 channels-last (random-init resnet34 on synthetic images, /std)",
-                       "parallelism": f"rays sharded: {world} target view(s), one per GPU, one NCCL all-gather of (rgb,depth) per step",
-                       "l2": "flushed between timed steps (256 MiB write); feature maps+weights are re-read from HBM each step"},
-            "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rays * 8 * 4,
-                    "d2h_bytes_per_step": n_rays * 4 * 4},
-            "gpu_launches": launches * args.steps * 2,   # device loop + e2e loop
+            "config": cfg,
+            "parallelism": {"rays_per_gpu": my_rays, "sharding": f"dist.ShardedRenderer: one image split into {world} ray slice(s), "
+                            "weights + encoded scene replicated, one NCCL all-gather of (rgb,depth) = 16 B/ray per step inside the timed region",
+                            "sharded_equals_single_gpu": parity,
+                            "l2": "flushed between timed steps (256 MiB write); feature maps + weights are re-read from HBM each step"},
+            "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": world * n_rays * 8 * 4,
+                    "d2h_bytes_per_step": world * n_rays * 4 * 4,
+                    "note": "every rank copies the image's rays from pinned host memory and reads the gathered image back"},
+            "gpu_launches": launches * args.steps * 2 * world,   # device loop + e2e loop, all ranks
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": ncu_traffic(),
+                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": traffic,
+                         "traffic_source": f"cited from capture {capture} (ncu --set full of this kernel on this workload), not measured by this run",
                          "kernel": "pair::field_pair_kernel<3> (fused projection + gather + PE + ResnetFC, tcgen05 cta_group::2), 2 launches per step",
                          "peak_kind": f"{pk['source']} sustained bf16 (kernel timed inside a long step); burst {pk['bf16_burst']}",
                          "frac_of_burst": (achieved / pk["bf16_burst"]) if achieved else None,
-                         "kernel_ms_per_step": field_total_ms / args.steps},
+                         "kernel_ms_per_step": field_total_ms / args.steps, "timing": roofline_pass,
+                         "flops": "algorithmic = executed (C = 512: nothing is pre-projected on this workload)"},
             "cpu_baseline": cpu,
         }
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
+        if train is not None:
+            line["train_step"] = train
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def oracle_inputs(scene, latent_cpu):
-    from oracle import pixelnerf_oracle as O
-    import pixel_nerf_yolo_b200.synth as synth
-    sc = O.encode_cameras(latent_cpu, scene["poses"], scene["focal"], scene["image_wh"])
-    return O, sc, synth.mlp_state(1), synth.mlp_state(2)
-
-
-def time_oracle(O, sc, mc, mf, rays, seed=0, chunk=1024):
-    """Wall time of the oracle render of `rays`, in ray chunks of `chunk` (the reference chunks its model calls too,
-    nerf.py:209-222; rays are independent, so the arithmetic per ray is the same) to bound host memory."""
-    total = 0.0
-    for s in range(0, rays.shape[1], chunk):
-        r = rays[:, s:s + chunk]
-        noise = O.RenderNoise.draw(r.shape[1], KC, KF, KFD, generator=torch.Generator().manual_seed(seed + s))
-        t0 = time.perf_counter()
-        O.render(sc, mc, mf, r, noise, n_coarse=KC, n_fine=KF, n_fine_depth=KFD, white_bkgd=True)
-        total += time.perf_counter() - t0
-    return total
-
-
-def cpu_baseline(scene, net, sample_rays):
-    """The oracle port on the host cores, bounded sample of the same workload."""
-    import pixel_nerf_yolo_b200.synth as synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    O, sc, mc, mf = oracle_inputs(scene, net.encoder.latent.detach().float().cpu())
-    rays = synth.target_rays(SIZE)[:, :: max(1, (SIZE * SIZE) // sample_rays)][:, :sample_rays]
-    time_oracle(O, sc, mc, mf, rays[:, :64])                                              # warm-up
-    dt = time_oracle(O, sc, mc, mf, rays)
-    return {"value": rays.shape[1] / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{rays.shape[1]} rays of the same 128x128 view (every {(SIZE * SIZE) // sample_rays}th ray), {dt:.1f} s, torch {torch.__version__} fp32, {cores} threads"}
-
-
 def run_reference(args):
-    """Reference arm: the reference's CPU path (oracle port) on all host threads; rank 0 only."""
+    """Reference arm: the UNMODIFIED reference's NeRFRenderer.forward on all host threads (rank 0 only), a bounded ray
+    sample of the same image per step."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import pixel_nerf_yolo_b200.synth as synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    scene = synth.scene_config1(seed=0, num_views=NS, C=C_LAT, size=SIZE)
-    O, sc, mc, mf = oracle_inputs(scene, scene["latent"])
     n = args.cpu_rays
-    rays = synth.target_rays(SIZE)[:, :: max(1, (SIZE * SIZE) // n)][:, :n]
-    for _ in range(args.warmup):
-        time_oracle(O, sc, mc, mf, rays[:, :64])
-    dt = sum(time_oracle(O, sc, mc, mf, rays, seed=i) for i in range(args.steps))
-    val = n * args.steps / dt
+    built = build_reference(torch.device("cpu"))
+    if built is not None:
+        render_par, rays, R = built
+        sub, stride = sample_rays(rays, n)
+        dt = time_reference_cpu(render_par, sub, args.steps, args.warmup)
+        kind, what = "reference", "unmodified reference (baseline/_ref) NeRFRenderer.forward"
+    else:
+        b = cpu_baseline_port(n)
+        dt, kind, what = n / b["value"] * args.steps, "port", "oracle port (baseline/_ref missing)"
+        sub = torch.empty(1, n, 8)
+    val = sub.shape[1] * args.steps / dt
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     print(json.dumps({
-        "impl": "reference", "metric": "rays/sec (samples/sec) 3-view render at 1/2/4/8 B200 vs host-CPU ref", "value": val,
-        "unit": "rays/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "step": f"bounded sample: {n} rays of the 16384-ray image per step"},
-        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} rays x {args.steps} steps, oracle port of the reference path, torch {torch.__version__} fp32"},
+        "impl": "reference", "metric": METRIC, "value": val,
+        "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(world),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": f"{sub.shape[1]} rays of the 16384-ray image per step x {args.steps} steps, {what}, torch {torch.__version__} fp32, {cores} threads"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -314,6 +589,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=None,
                     help="rays in the bounded CPU sample (default 4096 for cpu_baseline = 10-15 s of CPU work, 512 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip config 4, the train step and the GPU eager baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.cpu_rays is None:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PNR_ABI_VERSION 2
+#define PNR_ABI_VERSION 3
 
 /* precision of the field function (PixelNeRFNet.forward) */
 #define PNR_PREC_FP32 0 /* SIMT fp32 operands + fp32 accumulate: the <=1e-4 "accumulate-only" check build */
@@ -81,6 +81,9 @@ typedef struct pnr_points {
   int32_t mode;       /* 0 explicit points, 1 rays x depths                                          */
   int32_t P;          /* points per object (mode 1: B*K)                                             */
   int32_t K;          /* mode 1: samples per ray                                                     */
+  int64_t total;      /* points the buffers above hold in all (xyz: total x 3, z: total); every entry point  */
+                      /* requires total == scene->SB * P, so a scene encoded for more objects than the       */
+                      /* caller's batch cannot run past the buffers                                           */
 } pnr_points;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -129,6 +132,13 @@ int pnr_pyramid_pack(const float* const* levels, const int32_t* level_C, const i
  * sampling, PixelNerfTrainer.py:100-117) and rays (n_out, 8). */
 int pnr_gen_rays(const float* poses, const long long* pix_inds, float* rays, long long n_out, int N, int H, int W,
                  float fx, float fy, float cx, float cy, float z_near, float z_far, void* stream);
+
+/* util.gen_rays_yolo (src/util/util.py:808-876): rays through the cell centres (+0.49) of a W x H detection grid for N
+ * cameras given as world-to-camera extrinsics.  inv_intr (3,3) and inv_extr (N,4,4) are the inverses the reference computes with
+ * torch.inverse (the caller does the same on the host side; a 3x3 / 4x4 inverse is not kernel work); rays (N, H, W, 8) =
+ * [origin = inv_extr[:3,3], dir = inv_extr[:3,:3] . (inv_intr . [x+0.49, y+0.49, 1]) (NOT normalised), z_near, z_far]. */
+int pnr_gen_rays_yolo(const float* inv_intr, const float* inv_extr, float* rays, int N, int H, int W, float z_near,
+                      float z_far, void* stream);
 
 /* ---- output side ------------------------------------------------------------------------------------------- */
 /* eval/eval.py:283-290: rgb (B,3) -> rgb_u8 (B,3) = uint8(clamp(rgb,0,1)*255); depth (B) -> depth_norm (B) =
@@ -238,6 +248,14 @@ int pnr_sample_fine_depth_backward(const float* z_sorted, const float* d_z_sorte
 typedef struct pnr_render_args {
   const pnr_scene* scene;
   const float* rays; int32_t B;                    /* rays per object */
+  int64_t total_rays;                              /* rows of `rays` / the noise / output buffers; must equal scene->SB * B */
+  const pnr_scene* scene_fine;                     /* scene of the fine pass if it differs (lin_z pre-projections of the fine
+                                                      network, PNR_SCENE_PROJECTED); NULL = `scene` */
+  int32_t n_splits;                                /* 0 = automatic.  > 1: the ray batch is rendered as that many independent
+                                                      slices on forked streams, so that the tail wave of one field launch
+                                                      overlaps the head of the next (matters for small batches, e.g. one
+                                                      2 048-ray shard of an image; results are bit-identical, rays are
+                                                      independent).  Only for scene->SB == 1. */
   const float* steps;                              /* linspace(0, 1 - 1/Kc, Kc), see pnr_sample_coarse */
   const float* noise_coarse; const float* noise_u; const float* noise_jitter; const float* noise_gauss;
   const pnr_mlp_params* mlp_coarse; const void* packed_coarse;
@@ -264,31 +282,6 @@ int pnr_resnetfc_forward(const pnr_mlp_params* p, const float* zx, long long row
 
 /* Number of kernels the last pnr_* call on this thread launched (for bench.py's gpu_launches). */
 int pnr_last_launch_count(void);
-
-/* tcgen05 building-block self test: D(128 x N) = A(128 x K) * B(N x K)^T with bf16 operands staged
- * exactly like the fused kernel (bulk-copied pre-swizzled A, thread-written swizzled B, TMEM
- * accumulator, tcgen05.ld epilogue).  a (128,K), b (N,K) fp32 device inputs, d (128,N) fp32 device
- * output; workspace: K/64 * 16 KiB, 1024-byte aligned.  N in {16,32,48,64}, K multiple of 64 <= 512. */
-int pnr_umma_selftest(const float* a, const float* b, float* d, void* workspace, int N, int K, void* stream);
-
-/* Design-aid micro-benchmark: per-SM cp.async.bulk ingest (16 KiB stages, `depth`-slot ring, `grid` CTAs streaming
- * `n_stages` stages each from a buffer of `src_stages` stages).  out[grid] = elapsed SM cycles per CTA. */
-int pnr_ingest_bench(const void* src, int src_stages, int n_stages, int depth, int grid, long long* out,
-                     int n_prod, int n_cons, int stage_bytes, void* stream);
-
-/* Same through a 2-D tensor map (cp.async.bulk.tensor.2d), box = 64 x box_rows bf16, optional 128B swizzle. */
-int pnr_ingest_bench_tma(const void* src, int src_stages, int n_stages, int depth, int grid, long long* out,
-                         int box_rows, int swizzle, void* stream);
-
-/* Design-aid micro-benchmark: cycles for `iters` x 8 tcgen05.mma (kind::f16, bf16, K=16) of shape M x N issued
- * back to back from shared-memory operands.  out[grid] = elapsed SM cycles per CTA. */
-int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid, long long* out, int commit_every,
-                   void* stream);
-
-/* Design-aid micro-benchmark: distributed-shared-memory ping-pong of `bytes` between the two CTAs of a cluster.
- * mode 0: st.shared::cluster.v4 by `warps` warps + proxy fence + remote arrive; mode 1: one cp.async.bulk smem->peer smem.
- * out[2] = elapsed SM cycles per CTA for `iters` one-way transfers. */
-int pnr_dsmem_bench(int mode, int bytes, int iters, int warps, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -401,6 +401,26 @@ def gen_rays(poses: torch.Tensor, width: int, height: int, focal, z_near: float,
     return torch.cat((centers, dirs, near, far), dim=-1)
 
 
+def gen_rays_yolo(poses_w2c: torch.Tensor, width: int, height: int, focal, c, z_near: float, z_far: float) -> torch.Tensor:
+    """util.py:808-876: rays through (x + 0.49, y + 0.49) of a width x height cell grid for world-to-camera extrinsics:
+    direction = inv(E)[:3,:3] . inv(K) . [x+0.49, y+0.49, 1] (not normalised), origin = inv(E)[:3,3].  (N, H, W, 8)."""
+    K = torch.tensor([[float(focal[0]), 0.0, float(c[0])], [0.0, float(focal[1]), float(c[1])], [0.0, 0.0, 1.0]])
+    Kinv = torch.inverse(K)                                                  # :818-821
+    gx, gy = torch.meshgrid(torch.linspace(0, width - 1, width), torch.linspace(0, height - 1, height), indexing="ij")
+    pix = torch.stack([gx + 0.49, gy + 0.49, torch.ones_like(gx)], dim=2).view(-1, 3)      # :824-835, x-major order
+    d_cam = torch.matmul(Kinv, pix.t()).t()                                  # :838
+    near = torch.full((height * width, 1), float(z_near))
+    far = torch.full((height * width, 1), float(z_far))
+    rays = []
+    for i in range(poses_w2c.shape[0]):
+        Einv = torch.inverse(poses_w2c[i])                                   # :853
+        d_world = torch.matmul(Einv[:3, :3], d_cam.t()).t()                  # :857
+        o = Einv[:3, 3].repeat(height * width, 1)                            # :860-863
+        ray = torch.cat([o, d_world, near, far], dim=1).view(width, height, 8).permute(1, 0, 2)   # :866-872
+        rays.append(ray)
+    return torch.stack(rays)
+
+
 def yolo_render(scene: Scene, mlp: Dict[str, torch.Tensor], rays: torch.Tensor, noise: torch.Tensor, *,
                 n_coarse: int = 128, num_anchors: int = 3, **field_kw) -> torch.Tensor:
     """YoloRenderer.forward (src/render/yolo.py:37-114).  rays (B, 8), noise (B, Kc) -> (B, anchors, 7)."""

@@ -26,14 +26,16 @@ SCENE_TRAIN_TF32 = 8
 EXPORTS = [
     "pnr_version", "pnr_last_error", "pnr_device_supported", "pnr_sample_coarse", "pnr_composite",
     "pnr_sample_fine", "pnr_pack_features", "pnr_gather_encode", "pnr_mlp_pack_bytes", "pnr_mlp_pack",
-    "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_umma_selftest",
+    "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_gen_rays_yolo",
     "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
-    "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench",
     "pnr_field_tape_bytes", "pnr_field_forward_train", "pnr_field_backward_workspace_bytes", "pnr_field_backward",
     "pnr_composite_backward", "pnr_sample_fine_depth_backward", "pnr_pyramid_pack", "pnr_gen_rays", "pnr_yolo_reduce", "pnr_image_output", "pnr_rgb_loss",
     "pnr_mlp_pack_projected_bytes", "pnr_mlp_pack_projected", "pnr_project_features",
     "pnr_render_workspace_bytes", "pnr_render_forward",
 ]
+# lab equipment (csrc/pnr_lab.h, internal): micro-benchmarks and the tcgen05 self test; not part of the product ABI
+LAB_EXPORTS = ["pnr_umma_selftest", "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench"]
+ABI_VERSION = 3
 
 
 class Scene(C.Structure):
@@ -45,7 +47,26 @@ class Scene(C.Structure):
 
 class Points(C.Structure):
     _fields_ = [("xyz", C.c_void_p), ("dirs", C.c_void_p), ("rays", C.c_void_p), ("z", C.c_void_p),
-                ("mode", C.c_int32), ("P", C.c_int32), ("K", C.c_int32)]
+                ("mode", C.c_int32), ("P", C.c_int32), ("K", C.c_int32), ("total", C.c_int64)]
+
+
+def points_xyz(xyz: "torch.Tensor", dirs: Optional["torch.Tensor"]) -> Points:
+    """pnr_points over explicit world points xyz (SB, P, 3) (+ view directions); ``total`` comes from the tensor itself, so
+    the library can refuse a scene that was encoded for a different number of objects."""
+    pts = Points()
+    pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = xyz.data_ptr(), (None if dirs is None else dirs.data_ptr()), 0, xyz.shape[1], 0
+    pts.total = xyz.shape[0] * xyz.shape[1]
+    return pts
+
+
+def points_rays(rays: "torch.Tensor", z: "torch.Tensor", sb: int) -> Points:
+    """pnr_points over rays (SB*B, 8) x sample depths z (SB*B, K): point (b, k) = o + z[b, k] d."""
+    pts = Points()
+    Bt, K = z.shape
+    assert rays.shape[0] == Bt and Bt % max(sb, 1) == 0
+    pts.rays, pts.z, pts.mode, pts.P, pts.K = rays.data_ptr(), z.data_ptr(), 1, (Bt // max(sb, 1)) * K, K
+    pts.total = Bt * K
+    return pts
 
 
 class MlpParams(C.Structure):
@@ -67,7 +88,8 @@ class MlpGrads(C.Structure):
 
 class RenderArgs(C.Structure):
     """pnr_render_args: NeRFRenderer.forward as one C call."""
-    _fields_ = [("scene", C.POINTER(Scene)), ("rays", C.c_void_p), ("B", C.c_int32), ("steps", C.c_void_p),
+    _fields_ = [("scene", C.POINTER(Scene)), ("rays", C.c_void_p), ("B", C.c_int32), ("total_rays", C.c_int64),
+                ("scene_fine", C.POINTER(Scene)), ("n_splits", C.c_int32), ("steps", C.c_void_p),
                 ("noise_coarse", C.c_void_p), ("noise_u", C.c_void_p), ("noise_jitter", C.c_void_p), ("noise_gauss", C.c_void_p),
                 ("mlp_coarse", C.POINTER(MlpParams)), ("packed_coarse", C.c_void_p),
                 ("mlp_fine", C.POINTER(MlpParams)), ("packed_fine", C.c_void_p),
@@ -146,10 +168,11 @@ def load() -> C.CDLL:
     lib.pnr_rgb_loss.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp]
     lib.pnr_yolo_reduce.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.pnr_gen_rays.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, f32, f32, f32, f32, f32, f32, vp]
-    for name in EXPORTS:
+    lib.pnr_gen_rays_yolo.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp]
+    for name in EXPORTS + LAB_EXPORTS:
         getattr(lib, name)          # AttributeError here = header and library disagree
-    if lib.pnr_version() != 2:
-        raise NativeLibraryError(f"ABI version mismatch: library {lib.pnr_version()}, binding 2")
+    if lib.pnr_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI version mismatch: library {lib.pnr_version()}, binding {ABI_VERSION}")
     _lib = lib
     return lib
 

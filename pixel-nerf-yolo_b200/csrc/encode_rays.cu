@@ -137,6 +137,32 @@ rgb_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, flo
   }
 }
 
+// util.gen_rays_yolo (src/util/util.py:808-876): one thread per ray.  pixel = (x + 0.49, y + 0.49, 1) (grid of cell indices,
+// :826-835), camera-space direction = inv(K) . pixel (:838), world direction = inv(E)[:3,:3] . dir (:857, not normalised),
+// origin = inv(E)[:3,3] (:860).  The two products are written out as the fused multiply-add chains of a row-times-column dot
+// product (what the sgemm behind torch.matmul does for a K=3 contraction up to its internal order).
+__global__ void gen_rays_yolo_kernel(const float* __restrict__ inv_intr, const float* __restrict__ inv_extr, float* __restrict__ rays,
+                                     int N, int H, int W, float z_near, float z_far) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * H * W) return;
+  const int x = (int)(i % W);
+  const int y = (int)((i / W) % H);
+  const int n = (int)(i / ((long long)W * H));
+  const float px = (float)x + 0.49f, py = (float)y + 0.49f;
+  float dc[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) dc[r] = fmaf(inv_intr[r * 3 + 2], 1.0f, fmaf(inv_intr[r * 3 + 1], py, inv_intr[r * 3 + 0] * px));
+  const float* E = inv_extr + (size_t)n * 16;
+  float* o = rays + i * 8;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    o[r] = E[r * 4 + 3];
+    o[3 + r] = fmaf(E[r * 4 + 2], dc[2], fmaf(E[r * 4 + 1], dc[1], E[r * 4 + 0] * dc[0]));
+  }
+  o[6] = z_near;
+  o[7] = z_far;
+}
+
 }  // namespace pnr
 
 using namespace pnr;
@@ -177,6 +203,17 @@ extern "C" int pnr_gen_rays(const float* poses, const long long* pix_inds, float
   gen_rays_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses, pix_inds, rays, n_out, N, H, W, fx,
                                                                                     fy, cx, cy, z_near, z_far);
   PNR_CHECK_LAUNCH("gen_rays_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_gen_rays_yolo(const float* inv_intr, const float* inv_extr, float* rays, int N, int H, int W, float z_near,
+                                 float z_far, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(inv_intr && inv_extr && rays, PNR_ERR_ARG, "pnr_gen_rays_yolo: null pointer");
+  PNR_REQUIRE(N >= 1 && H >= 1 && W >= 1, PNR_ERR_ARG, "pnr_gen_rays_yolo: bad shape");
+  const long long n = (long long)N * H * W;
+  gen_rays_yolo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(inv_intr, inv_extr, rays, N, H, W, z_near, z_far);
+  PNR_CHECK_LAUNCH("gen_rays_yolo_kernel");
   return PNR_OK;
 }
 

@@ -171,6 +171,9 @@ int validate_scene_points(const pnr_scene* sc, const pnr_points* q, const char* 
               "%s: bad scene shape SB=%d NS=%d C=%d Hl=%d Wl=%d", who, sc->SB, sc->NS, sc->C, sc->Hl, sc->Wl);
   PNR_REQUIRE(sc->C % 8 == 0, PNR_ERR_UNSUPPORTED, "%s: latent channels must be a multiple of 8 (got %d)", who, sc->C);
   PNR_REQUIRE(q->P >= 0, PNR_ERR_ARG, "%s: negative point count", who);
+  PNR_REQUIRE(q->total == (long long)sc->SB * q->P, PNR_ERR_ARG,
+              "%s: the point buffers hold %lld points but the scene has SB=%d objects x P=%d points (encode() and the ray batch disagree?)",
+              who, (long long)q->total, sc->SB, q->P);
   if (q->mode == 0) PNR_REQUIRE(q->xyz || q->P == 0, PNR_ERR_ARG, "%s: xyz is null", who);
   else if (q->mode == 1) {
     PNR_REQUIRE((q->rays && q->z) || q->P == 0, PNR_ERR_ARG, "%s: rays/z is null", who);

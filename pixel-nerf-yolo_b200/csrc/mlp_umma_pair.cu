@@ -943,77 +943,3 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
 }
 
 }  // namespace pnr
-
-// ---- micro-benchmark: DSMEM ping-pong of `bytes` between the two CTAs of a cluster (design aid) ------------------
-// mode 0: st.shared::cluster.v4 by `warps` warps + fence.proxy.async.shared::cluster + relaxed remote arrive
-// mode 1: one cp.async.bulk.shared::cluster.shared::cta (TMA engine) completing on the peer's mbarrier
-namespace pnr {
-__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
-               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
-}
-__global__ void __launch_bounds__(256, 1) dsmem_pingpong_kernel(int mode, int bytes, int iters, int warps, long long* out) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar = sbase + 2 * 65536;            // [0,64K) send buffer, [64K,128K) receive buffer
-  if (threadIdx.x == 0) { mbar_init(bar, mode == 0 ? warps : 1); fence_barrier_init(); }
-  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = i;
-  __syncthreads();
-  cluster_sync_all();
-  const uint32_t peer_recv = mapa_u32(sbase + 65536, peer), peer_bar = mapa_u32(bar, peer);
-  const long long t0 = clock64();
-  uint32_t par = 0;
-  for (int it = 0; it < iters; ++it) {
-    const bool my_turn = ((it & 1) == (int)rank);    // rank 0 sends on even iterations, rank 1 on odd ones
-    if (my_turn) {
-      if (mode == 0) {
-        if (warp < warps) {
-          for (int off = (warp * 32 + lane) * 16; off < bytes; off += warps * 32 * 16) {
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + off);
-            st_cluster_v4(peer_recv + off, v.x, v.y, v.z, v.w);
-          }
-          fence_proxy_async_cluster();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(peer_bar);
-        }
-      } else if (threadIdx.x == 0) {
-        fence_proxy_async();
-        mbar_expect_tx_cluster(peer_bar, bytes);
-        bulk_s2s(peer_recv, sbase, bytes, peer_bar);
-      }
-    } else {
-      mbar_wait_cluster(bar, par);
-      par ^= 1;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
-  cluster_sync_all();
-}
-}  // namespace pnr
-
-extern "C" int pnr_dsmem_bench(int mode, int bytes, int iters, int warps, long long* out, void* stream) {
-  using namespace pnr;
-  reset_launch_count();
-  PNR_REQUIRE(out && bytes >= 1024 && bytes <= 65536 && bytes % 512 == 0 && warps >= 1 && warps <= 8 && iters > 0, PNR_ERR_ARG,
-              "pnr_dsmem_bench: bad arguments");
-  const int smem = 2 * 65536 + 64;
-  cudaError_t e = cudaFuncSetAttribute(dsmem_pingpong_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3(2); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, dsmem_pingpong_kernel, mode, bytes, iters, warps, out);
-  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "dsmem_pingpong_kernel launch: %s", cudaGetErrorString(e));
-  PNR_CHECK_LAUNCH("dsmem_pingpong_kernel");
-  return PNR_OK;
-}

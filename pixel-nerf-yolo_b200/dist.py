@@ -68,20 +68,59 @@ def slice_noise(noise: Optional[Dict[str, torch.Tensor]], sb: int, b_total: int,
     return out
 
 
+def draw_render_noise(n_rays: int, n_coarse: int, n_fine: int, n_fine_depth: int, device) -> Dict[str, Optional[torch.Tensor]]:
+    """The four noise draws of one ``NeRFRenderer.forward`` in the reference's order (nerf.py:117,141,147,164) for the FULL
+    ray batch.  Ranks that seed their generators equally draw equal tensors, so slicing them makes the N-GPU render equal the
+    1-GPU render of the same seed bit for bit."""
+    kf, kfd = n_fine - n_fine_depth, n_fine_depth
+    out: Dict[str, Optional[torch.Tensor]] = {"coarse": torch.rand(n_rays, n_coarse, device=device, dtype=torch.float32),
+                                              "fine_u": None, "fine_jitter": None, "depth": None}
+    if n_fine > 0:
+        if kf > 0:
+            out["fine_u"] = torch.rand(n_rays, kf, dtype=torch.float32, device=device)
+            out["fine_jitter"] = torch.rand_like(out["fine_u"])
+        if kfd > 0:
+            out["depth"] = torch.randn(n_rays, kfd, dtype=torch.float32, device=device)
+    return out
+
+
 class ShardedRenderer(torch.nn.Module):
     """One process per GPU (torchrun).  ``render_fn(rays_slice, noise_slice) -> (rgb (SB,b,3), depth (SB,b))``
-    is the local single-GPU render; every rank receives the full (SB, B, 3)/(SB, B) result."""
+    is the local single-GPU render; every rank receives the full (SB, B, 3)/(SB, B) result.  ``noise_fn(n_rays)``
+    (optional) draws the full-batch noise when the caller passes none (see ``draw_render_noise``)."""
 
-    def __init__(self, render_fn: Callable, group=None, tile: int = RAY_TILE):
+    def __init__(self, render_fn: Callable, group=None, tile: int = RAY_TILE, noise_fn: Optional[Callable] = None):
         super().__init__()
         self.render_fn = render_fn
         self.group = group
         self.tile = tile
+        self.noise_fn = noise_fn
+
+    @classmethod
+    def for_renderer(cls, renderer, net, group=None):
+        """The sharded equivalent of ``renderer.bind_parallel(net, gpus, simple_output=True)`` under torchrun."""
+        wrapped = renderer.bind_parallel(net, None, simple_output=True).eval()
+
+        def render_fn(rays, noise):
+            renderer.noise_override = noise
+            try:
+                with torch.no_grad():
+                    return wrapped(rays)
+            finally:
+                renderer.noise_override = None
+
+        def noise_fn(n):
+            return draw_render_noise(n, renderer.n_coarse, renderer.n_fine if renderer.using_fine else 0,
+                                     renderer.n_fine_depth if renderer.using_fine else 0, next(net.parameters()).device)
+
+        return cls(render_fn, group=group, noise_fn=noise_fn)
 
     def forward(self, rays: torch.Tensor, noise: Optional[Dict[str, torch.Tensor]] = None):
         world = dist.get_world_size(self.group)
         rank = dist.get_rank(self.group)
         sb, b_total = rays.shape[0], rays.shape[1]
+        if noise is None and self.noise_fn is not None:
+            noise = self.noise_fn(sb * b_total)
         bounds = shard_bounds(b_total, world, self.tile)
         s, e = bounds[rank]
         if e > s:
@@ -95,10 +134,15 @@ class ShardedRenderer(torch.nn.Module):
 
 
 class MultiDeviceRenderer(torch.nn.Module):
-    """Single-process multi-device driver behind ``NeRFRenderer.bind_parallel(net, gpus)``: the wrapped
-    ``_RenderWrapper`` is replicated to every device once; its encoded scene and parameters are re-copied
-    only when they changed (new ``encode`` / optimizer step); each call launches one ray slice per device
-    asynchronously and gathers the outputs on the first device with peer copies over NVLink."""
+    """Single-process multi-device driver behind ``NeRFRenderer.bind_parallel(net, gpus)`` (nerf.py:373-377, the
+    reference's ``DataParallel(dim=1)``): the NETWORK is replicated to every device once and re-copied only when its
+    state changed (new ``encode`` / new weights, tracked by explicit generation counters: ``net.render_state_key()``);
+    the renderer object is shared, so its sampling settings are always current.  Each call launches one ray slice per
+    device asynchronously and gathers the outputs on the first device with peer copies over NVLink.
+
+    Inference only: the reference's DataParallel also reduces the replicas' gradients onto GPU 0 in backward; this
+    driver does not, so a call that would record a backward pass raises (train with one process per GPU and
+    ``dist.GradientSync``)."""
 
     def __init__(self, wrapped, gpus: Sequence[int]):
         super().__init__()
@@ -107,34 +151,59 @@ class MultiDeviceRenderer(torch.nn.Module):
         self._replicas = None
         self._key = None
 
-    def _state_key(self):
-        net = self.module.net
-        return (tuple((p.data_ptr(), p._version) for p in net.parameters()), net.encoder.latent.data_ptr(),
-                net.encoder.latent._version, net.poses.data_ptr(), net.poses._version)
+    def state_key(self):
+        """What the replicas depend on; compared by value, never by pointer identity."""
+        return self.module.net.render_state_key()
+
+    def invalidate(self):
+        """Force re-replication on the next call (after editing weights through ``p.data`` etc.)."""
+        self._key = None
 
     def _sync(self):
-        key = self._state_key()
+        key = self.state_key()
         if self._replicas is not None and key == self._key:
             return
+        from .render.nerf import _RenderWrapper
         src = self.module.net
         reps = [self.module]
         for d in self.devices[1:]:
-            with torch.cuda.device(d):
-                r = copy.deepcopy(self.module).to(d)
-                r.net.encoder.set_latent(src.encoder.latent.to(d))
-                r.net.num_objs, r.net.num_views_per_obj = src.num_objs, src.num_views_per_obj
-                r.net._cam_cache = None
-            reps.append(r)
+            with torch.cuda.device(d), torch.no_grad():
+                latent = src.encoder._latent
+                src.encoder._latent = None if latent is None else latent.detach()     # deepcopy only copies graph leaves
+                try:
+                    net = copy.deepcopy(src)
+                finally:
+                    src.encoder._latent = latent
+                net = net.to(d)
+                net.requires_grad_(False)
+                net.num_objs, net.num_views_per_obj = src.num_objs, src.num_views_per_obj
+                net._cam_cache = None
+                net._field_ws = None
+            reps.append(_RenderWrapper(net, self.module.renderer, self.module.simple_output))
         self._replicas, self._key = reps, key
 
     def forward(self, rays, want_weights=False):
+        net = self.module.net
+        if torch.is_grad_enabled() and (net._wants_grad(True) or net._wants_grad(False)):
+            raise NotImplementedError(
+                "MultiDeviceRenderer (bind_parallel(net, gpus) with several GPUs) is an inference driver: gradients of the "
+                "replicas are not reduced onto the bound network.  Train with one process per GPU (torchrun) and "
+                "dist.GradientSync, or call under torch.no_grad().")
         self._sync()
+        renderer = self.module.renderer
         sb, b_total = rays.shape[0], rays.shape[1]
         bounds = shard_bounds(b_total, len(self.devices))
+        full_noise = renderer.noise_override
         outs = []
-        for rep, d, (s, e) in zip(self._replicas, self.devices, bounds):
-            with torch.cuda.device(d):
-                outs.append(rep(rays[:, s:e].to(d, non_blocking=True), want_weights=want_weights))
+        try:
+            for rep, d, (s, e) in zip(self._replicas, self.devices, bounds):
+                with torch.cuda.device(d):
+                    if full_noise is not None:
+                        nz = slice_noise(full_noise, sb, b_total, s, e)
+                        renderer.noise_override = {k: (None if v is None else v.to(d, non_blocking=True)) for k, v in nz.items()}
+                    outs.append(rep(rays[:, s:e].to(d, non_blocking=True), want_weights=want_weights))
+        finally:
+            renderer.noise_override = full_noise
         d0 = self.devices[0]
         if isinstance(outs[0], tuple):
             return tuple(torch.cat([o[i].to(d0, non_blocking=True) for o in outs], dim=1) for i in range(2))

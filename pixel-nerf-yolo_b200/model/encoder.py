@@ -64,6 +64,8 @@ class SpatialEncoder(nn.Module):
         self._levels = None          # pyramid levels of the last inference forward (latent not materialised yet)
         self.register_buffer("latent_scaling", torch.empty(2, dtype=torch.float32), persistent=False)
         self._packed = {}
+        self.generation = 0          # bumped whenever the encoded maps change (set_latent / set_levels / .to()): cache keys use
+                                     # it instead of (data_ptr, _version), which the caching allocator can hand out again
 
     # ``latent`` (N, C, Hl, Wl) fp32 NCHW, the reference's attribute (encoder.py:77,168).  After an inference forward it
     # is built lazily from the pyramid levels (the hot path never needs it).
@@ -86,6 +88,7 @@ class SpatialEncoder(nn.Module):
         if self._levels is not None:
             self._levels = [fn(l) for l in self._levels]
         self._packed = {}
+        self.generation += 1
         return self
 
     # ---- channels-last caches --------------------------------------------------------------------------
@@ -97,6 +100,7 @@ class SpatialEncoder(nn.Module):
         ls = torch.tensor([float(latent.shape[-1]), float(latent.shape[-2])], device=latent.device)
         self.latent_scaling = ls / (ls - 1) * 2.0
         self._packed = {}
+        self.generation += 1
 
     def set_levels(self, levels):
         """Install pyramid levels [(N, C_l, H_l, W_l)] without materialising the concatenated latent."""
@@ -107,6 +111,7 @@ class SpatialEncoder(nn.Module):
         ls = torch.tensor([float(w), float(h)], device=levels[0].device)
         self.latent_scaling = ls / (ls - 1) * 2.0
         self._packed = {}
+        self.generation += 1
 
     def latent_shape(self):
         """(N, C, Hl, Wl) without forcing the lazy latent into existence."""

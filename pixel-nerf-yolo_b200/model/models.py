@@ -26,14 +26,9 @@ class _FieldTrainFn(torch.autograd.Function):
         lib = _lib.load()
         dev = feat.device
         sc, keep = net._scene_for(feat, fp32_maps=True)
-        pts = _lib.Points()
-        if mode == "rays":          # a = rays (SB*B, 8), b = z (SB*B, K)
-            K = b.shape[1]
-            P = (a.shape[0] // sb) * K
-            pts.rays, pts.z, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 1, P, K
-        else:                       # a = xyz (SB, P, 3), b = viewdirs (SB, P, 3)
-            P = a.shape[1]
-            pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 0, P, 0
+        # mode "rays": a = rays (SB*B, 8), b = z (SB*B, K); mode "xyz": a = xyz (SB, P, 3), b = viewdirs (SB, P, 3)
+        pts = _lib.points_rays(a, b, sb) if mode == "rays" else _lib.points_xyz(a, b)
+        P = pts.P
         cp = mlp.c_params()
         out = torch.empty(sb, P, 4, device=dev, dtype=torch.float32)
         tape = torch.empty(lib.pnr_field_tape_bytes(sc, pts, cp), dtype=torch.uint8, device=dev)
@@ -54,11 +49,7 @@ class _FieldTrainFn(torch.autograd.Function):
         net, mlp, mode, sb, P = ctx.net, ctx.mlp, ctx.mode, ctx.sb, ctx.P
         dev = feat.device
         sc, _keep = net._scene_for(feat, fp32_maps=True, cams=ctx.keep)
-        pts = _lib.Points()
-        if mode == "rays":
-            pts.rays, pts.z, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 1, P, b.shape[1]
-        else:
-            pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = a.data_ptr(), b.data_ptr(), 0, P, 0
+        pts = _lib.points_rays(a, b, sb) if mode == "rays" else _lib.points_xyz(a, b)
         cp = mlp.c_params()
         grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
         need_feat, need_a, need_b = ctx.needs_input_grad[4], ctx.needs_input_grad[5], ctx.needs_input_grad[6]
@@ -138,6 +129,8 @@ class PixelNeRFNet(torch.nn.Module):
         self.train_precision = "fp32"
         self.fp32_chunk_points = 50000
         self._cam_cache = None
+        self._cam_gen = 0            # bumped by set_cameras (encode): part of render_state_key()
+        self._field_ws = None        # persistent view-mean scratch of the tcgen05 field kernel
 
     # ------------------------------------------------------------------------------------------------
     def encode(self, images, poses, focal, z_bounds=None, c=None):
@@ -182,6 +175,7 @@ class PixelNeRFNet(torch.nn.Module):
             c = c.unsqueeze(-1).repeat((1, 2))
         self.c = c.float().to(self.poses.device)
         self._cam_cache = None
+        self._cam_gen += 1
 
     # ------------------------------------------------------------------------------------------------
     def _scene(self, fp32_maps: bool):
@@ -222,6 +216,40 @@ class PixelNeRFNet(torch.nn.Module):
         sc.image_w, sc.image_h, sc.lat_scale_x, sc.lat_scale_y = iw, ih, lsx, lsy
         return sc, (poses, focal, center, iw, ih, lsx, lsy)
 
+    def projects_latent(self) -> bool:
+        """True when the tcgen05 path gathers lin_z PRE-PROJECTIONS of the maps (PNR_SCENE_PROJECTED): automatic for latents
+        wider than the hidden width (1 792-channel YOLO maps), or forced with ``project_wide_latent``."""
+        proj = self.project_wide_latent
+        if proj is None:
+            proj = self.mlp_coarse.d_latent > self.mlp_coarse.d_hidden
+        return bool(proj)
+
+    def _scene_bf16(self, mlp, proj: bool):
+        """pnr_scene of the tcgen05 path for one network: plain bf16 maps, or that network's lin_z pre-projections."""
+        if proj:
+            feat = mlp.project_features(self.encoder.packed_latent(fp32=True), self.encoder.generation)
+            sc, keep = self._scene_for(feat, fp32_maps=False)
+            sc.flags |= _lib.SCENE_PROJECTED
+            return sc, (keep, feat)
+        return self._scene(fp32_maps=False)
+
+    def render_scenes(self):
+        """(coarse scene, fine scene or None, keep-alives) for ``pnr_render_forward``: the two passes only differ when the
+        maps are pre-projected through each network's own lin_z."""
+        proj = self.projects_latent()
+        sc_c, keep_c = self._scene_bf16(self.mlp_coarse, proj)
+        if proj and self.mlp_fine is not None:
+            sc_f, keep_f = self._scene_bf16(self.mlp_fine, proj)
+            return sc_c, sc_f, (keep_c, keep_f)
+        return sc_c, None, (keep_c,)
+
+    def render_state_key(self):
+        """Everything a prepared ``pnr_render_args`` depends on: encoded maps, cameras, weights, precision switches.  Explicit
+        generation counters (not pointer identity, which the caching allocator re-issues)."""
+        mf = self.mlp_fine
+        return (self.encoder.generation, self._cam_gen, self.num_views_per_obj, self.projects_latent(), self.precision,
+                self.mlp_coarse._param_key(), None if mf is None else mf._param_key())
+
     def _mlp(self, coarse):
         return self.mlp_coarse if (coarse or self.mlp_fine is None) else self.mlp_fine
 
@@ -236,17 +264,12 @@ class PixelNeRFNet(torch.nn.Module):
         launches = 0
         with torch.cuda.device(dev):
             if self.precision == "bf16":
-                proj = self.project_wide_latent
-                if proj is None:
-                    proj = mlp.d_latent > mlp.d_hidden
-                if proj:
-                    feat = mlp.project_features(self.encoder.packed_latent(fp32=True))
-                    sc, keep2 = self._scene_for(feat, fp32_maps=False)
-                    sc.flags |= _lib.SCENE_PROJECTED
-                else:
-                    sc, keep2 = self._scene(fp32_maps=False)
+                proj = self.projects_latent()
+                sc, keep2 = self._scene_bf16(mlp, proj)
                 ws_bytes = lib.pnr_field_workspace_bytes(sc, pts, _lib.PREC_BF16)
-                ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)   # caching allocator: no cudaMalloc after the first call
+                ws = self._field_ws
+                if ws is None or ws.numel() < max(ws_bytes, 16) or ws.device != dev:
+                    ws = self._field_ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
                 rc = lib.pnr_field_forward(sc, pts, mlp.c_params(), mlp.packed(projected=proj).data_ptr(), out.data_ptr(),
                                            ws.data_ptr(), ws_bytes, _lib.PREC_BF16, self.code.num_freqs, self.code.freq_factor,
                                            _lib.stream_ptr(dev))
@@ -284,23 +307,23 @@ class PixelNeRFNet(torch.nn.Module):
         step = B if self.precision == "bf16" else max(1, self.fp32_chunk_points // max(SB * self.num_views_per_obj, 1))
         for b0 in range(0, max(B, 1), max(step, 1)):
             xs, ds = xyz[:, b0:b0 + step].contiguous(), viewdirs[:, b0:b0 + step].contiguous()
-            pts = _lib.Points()
-            pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = xs.data_ptr(), ds.data_ptr(), 0, xs.shape[1], 0
+            pts = _lib.points_xyz(xs, ds)
             outs.append(self._run_field(pts, SB, xs.shape[1], coarse, (xs, ds)))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
     def _wants_grad(self, coarse, *tensors):
-        """True when this call must record a backward pass (the reference just runs under autograd)."""
-        if not (torch.is_grad_enabled() and self.training):      # inference callers use .eval() and/or no_grad()
+        """True when this call must record a backward pass.  The reference simply runs under autograd, whatever the module's
+        train/eval mode: so does this -- gradient mode on and anything on the path requiring grad (query points / depths,
+        the network's parameters, the encoder's maps unless ``stop_encoder_grad``).  Inference callers wrap the call in
+        ``torch.no_grad()`` as the reference's eval scripts do (eval/eval.py:262, trainer.py vis/eval steps)."""
+        if not torch.is_grad_enabled():
             return False
-        if self.yolo:
-            raise NotImplementedError("PixelNeRFNet (B200 path): the YOLO head has no backward pass yet; run it under "
-                                      "torch.no_grad() / .eval()")
-        if any(t is not None and t.requires_grad for t in tensors):
-            return True
-        if any(p.requires_grad for p in self._mlp(coarse).parameters()):
-            return True
-        return self.encoder.latent.requires_grad and not self.stop_encoder_grad
+        want = any(t is not None and t.requires_grad for t in tensors)
+        want = want or any(p.requires_grad for p in self._mlp(coarse).parameters())
+        if not want and not self.stop_encoder_grad:
+            lat = self.encoder._latent
+            want = lat is not None and lat.requires_grad
+        return want
 
     def _train_feat(self):
         """fp32 channels-last view of encoder.latent that autograd can differentiate through (a permute + copy in
@@ -312,13 +335,8 @@ class PixelNeRFNet(torch.nn.Module):
 
     def fused_render_ready(self) -> bool:
         """True when NeRFRenderer can hand the whole forward to ``pnr_render_forward`` (one C call): bf16 tensor-core path,
-        NeRF head, one scene for both passes (no per-network lin_z pre-projection of wide latents)."""
-        if self.precision != "bf16" or self.yolo:
-            return False
-        proj = self.project_wide_latent
-        if proj is None:
-            proj = self.mlp_coarse.d_latent > self.mlp_coarse.d_hidden
-        return not proj
+        NeRF head."""
+        return self.precision == "bf16" and not self.yolo
 
     def field_from_rays(self, rays, z, coarse=True, sb=1):
         """Renderer fast path: evaluate the field at o + z*d for rays (SB*B, 8), z (SB*B, K) without ever
@@ -333,8 +351,7 @@ class PixelNeRFNet(torch.nn.Module):
             return _FieldTrainFn.apply(self, mlp, "rays", sb, self._train_feat(), rays.detach(), z,
                                        *mlp.ordered_params()).reshape(Bt, K, 4)
         if self.precision == "bf16":
-            pts = _lib.Points()
-            pts.rays, pts.z, pts.mode, pts.P, pts.K = rays.data_ptr(), z.data_ptr(), 1, Bp * K, K
+            pts = _lib.points_rays(rays, z, sb)
             return self._run_field(pts, sb, Bp * K, coarse, (rays, z)).reshape(Bt, K, self.d_out)
         # fp32 check path: bound the workspace by chunking rays (results do not depend on the chunking)
         step = max(1, self.fp32_chunk_points // max(K * self.num_views_per_obj * sb, 1))
@@ -343,8 +360,7 @@ class PixelNeRFNet(torch.nn.Module):
         for b0 in range(0, Bp, step):
             rc, zc = r3[:, b0:b0 + step].contiguous(), z3[:, b0:b0 + step].contiguous()
             n = rc.shape[1]
-            pts = _lib.Points()
-            pts.rays, pts.z, pts.mode, pts.P, pts.K = rc.data_ptr(), zc.data_ptr(), 1, n * K, K
+            pts = _lib.points_rays(rc.reshape(-1, 8), zc.reshape(-1, K), sb)
             outs.append(self._run_field(pts, sb, n * K, coarse, (rc, zc)).reshape(sb, n, K, self.d_out))
         return torch.cat(outs, dim=1).reshape(Bt, K, self.d_out)
 

@@ -59,6 +59,7 @@ class ResnetFC(nn.Module):
         self.activation = nn.ReLU()
         self._packed = None
         self._packed_key = None
+        self._generation = 0
 
     # ---- C-ABI views of the parameters --------------------------------------------------------------
     def c_params(self) -> "_lib.MlpParams":
@@ -96,7 +97,20 @@ class ResnetFC(nn.Module):
         return g
 
     def _param_key(self):
-        return tuple((q.data_ptr(), q._version) for q in self.parameters())
+        """Identity of the current weights: every derived cache (packed bf16 stream, lin_z pre-projections, render plans) is
+        keyed on it.  In-place updates through ``p.data`` do not bump ``p._version``: call ``invalidate()`` after those."""
+        return (self._generation,) + tuple((q.data_ptr(), q._version) for q in self.parameters())
+
+    def invalidate(self):
+        """Drop every cache derived from the parameters (call after editing weights behind autograd's back, e.g. ``p.data``)."""
+        self._generation += 1
+        self._packed = None
+        self._packed_proj = None
+        self._projected = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._generation += 1
 
     def packed(self, projected: bool = False) -> torch.Tensor:
         """bf16 tcgen05 weight stream + bias tables: a derived cache, rebuilt whenever a parameter changed
@@ -142,10 +156,10 @@ class ResnetFC(nn.Module):
             self._packed_proj = (key, blob)
         return self._packed_proj[1]
 
-    def project_features(self, feat_fp32_nhwc: torch.Tensor) -> torch.Tensor:
+    def project_features(self, feat_fp32_nhwc: torch.Tensor, feat_gen: int = 0) -> torch.Tensor:
         """(N, Hl, Wl, d_latent) fp32 channels-last encoder output -> (N, Hl, Wl, n_lin_z * d_hidden) bf16: slice b is the map
         pushed through ``lin_z[b]`` (no bias).  Cached per (parameters, map): recomputed after an optimizer step or encode."""
-        key = (self._param_key(), feat_fp32_nhwc.data_ptr(), feat_fp32_nhwc._version, tuple(feat_fp32_nhwc.shape))
+        key = (self._param_key(), feat_fp32_nhwc.data_ptr(), feat_fp32_nhwc._version, tuple(feat_fp32_nhwc.shape), feat_gen)
         hit = getattr(self, "_projected", None)
         if hit is None or hit[0] != key:
             lib = _lib.load()

@@ -1,5 +1,6 @@
-"""Ray generation: drop-in for ``util.gen_rays`` / ``util.unproj_map`` (src/util/util.py:115-145, 240-278), the step
-right before the renderer, as one kernel of the C-ABI library (``pnr_gen_rays``).
+"""Ray generation: drop-in for ``util.gen_rays`` / ``util.unproj_map`` (src/util/util.py:115-145, 240-278) and
+``util.gen_rays_yolo`` (:808-876), the step right before the renderer, as kernels of the C-ABI
+library (``pnr_gen_rays``, ``pnr_gen_rays_yolo``).
 
 ``pix_inds`` is an extension for the trainer's ray sampling (PixelNerfTrainer.py:100-117): instead of generating all
 N*H*W rays and indexing them, only the selected pixels' rays are produced.
@@ -47,6 +48,28 @@ def gen_rays(poses, width, height, focal, z_near, z_far, c=None, ndc=False, pix_
         rc = _lib.load().pnr_gen_rays(p.data_ptr(), idx_ptr, rays.data_ptr(), n_out, n, height, width, fx, fy, cx, cy,
                                       float(z_near), float(z_far), _lib.stream_ptr(dev))
     _lib.check(rc, "pnr_gen_rays")
+    return rays
+
+
+def gen_rays_yolo(poses, width, height, focal, c, z_near, z_far):
+    """Drop-in for ``util.gen_rays_yolo`` (src/util/util.py:808-876): poses (N, 4, 4) WORLD-TO-CAMERA extrinsics on a CUDA
+    device -> rays (N, H, W, 8) through the cell centres (+0.49) of a ``width x height`` detection grid; directions are not
+    normalised (as in the reference).  The two small matrix inverses are taken with ``torch.inverse`` like the reference
+    does; the per-ray arithmetic is one kernel (``pnr_gen_rays_yolo``)."""
+    _lib.require_cuda(poses, "poses")
+    _lib.require_device(poses.device)
+    dev = poses.device
+    fx, fy = _pair(focal)
+    cx, cy = _pair(c)
+    intr = torch.tensor([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]], dtype=torch.float32).to(dev)
+    inv_intr = torch.inverse(intr).contiguous()
+    inv_extr = torch.inverse(poses.detach().float()).contiguous()
+    n = poses.shape[0]
+    rays = torch.empty(n, height, width, 8, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pnr_gen_rays_yolo(inv_intr.data_ptr(), inv_extr.data_ptr(), rays.data_ptr(), n, height, width,
+                                           float(z_near), float(z_far), _lib.stream_ptr(dev))
+    _lib.check(rc, "pnr_gen_rays_yolo")
     return rays
 
 

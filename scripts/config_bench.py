@@ -42,7 +42,7 @@ def flop_per_ray(ns, c, kc, kf, h=512, d_in=42, d_out=4):
 
 def config3(train_precision="fp32"):
     scene = H.make_scene_dict(num_objs=4, num_views=3, feat=64, size=128)
-    net = H.build_net(scene, precision="bf16").train()
+    net = H.build_net(scene, precision="bf16", train=True)
     net.train_precision = train_precision
     lat = scene["latent"].to(dev).clone().requires_grad_(True)
     net.encoder.set_latent(lat)

@@ -41,8 +41,7 @@ def run(tag, feat_hw, size, n_points, iters=5):
     # points uniformly inside the unit cube around the origin (all three cameras look at it)
     xyz = ((torch.rand(1, n_points, 3, generator=g) - 0.5) * 0.9).to(dev).contiguous()
     dirs = torch.nn.functional.normalize(torch.randn(1, n_points, 3, generator=g), dim=-1).to(dev).contiguous()
-    pts = _lib.Points()
-    pts.xyz, pts.dirs, pts.mode, pts.P, pts.K = xyz.data_ptr(), dirs.data_ptr(), 0, n_points, 0
+    pts = _lib.points_xyz(xyz, dirs)
     rows = 3 * n_points
     lat = torch.empty(rows, C, dtype=torch.bfloat16, device=dev)
     zf = torch.empty(rows, 42, dtype=torch.float32, device=dev)

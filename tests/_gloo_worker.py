@@ -63,6 +63,18 @@ def main():
         rgb, depth = ShardedRenderer(fake_render)(rays, noise)
         ref_rgb, ref_depth = fake_render(rays, noise)
         assert torch.equal(rgb, ref_rgb) and torch.equal(depth, ref_depth), (sb, b)
+    # no noise passed: the renderer's noise_fn draws the FULL batch on every rank from equally seeded generators (the four
+    # draws of one NeRFRenderer.forward, nerf.py:117,141,147,164) and each rank takes its rows
+    from pixel_nerf_yolo_b200.dist import draw_render_noise
+    rays = torch.randn(1, 333, 8, generator=g)
+    noise_fn = lambda n: draw_render_noise(n, 4, 8, 4, "cpu")
+    torch.manual_seed(99)
+    rgb, depth = ShardedRenderer(fake_render, noise_fn=noise_fn)(rays)
+    torch.manual_seed(99)
+    full = noise_fn(333)
+    assert set(full) == {"coarse", "fine_u", "fine_jitter", "depth"} and full["fine_u"].shape == (333, 4) and full["depth"].shape == (333, 4)
+    ref_rgb, ref_depth = fake_render(rays, full)
+    assert torch.equal(rgb, ref_rgb) and torch.equal(depth, ref_depth)
     check_gradient_sync()
     dist.barrier()
     if dist.get_rank() == 0:

@@ -27,7 +27,7 @@ def check_data_parallel_train_step(dev):
     mse = torch.nn.functional.mse_loss
 
     def step(s, e):
-        net = H.build_net(scene, device=dev, precision="bf16").train()
+        net = H.build_net(scene, device=dev, precision="bf16", train=True)
         r = NeRFRenderer(64, 32, 16, white_bkgd=True).train().to(dev)
         r.noise_override = {k: v[s:e].contiguous() for k, v in noise.items()}
         res = r(net, rays[:, s:e].contiguous())

@@ -21,8 +21,10 @@ def make_scene_dict(num_objs=1, num_views=3, feat=16, size=128, seed=5, C=512):
     return synth.scene_config1(seed=seed, num_views=num_views, C=C, size=size, feat=feat, num_objs=num_objs)
 
 
-def build_net(scene, device="cuda", coarse_seed=1, fine_seed=2, precision="bf16", model_conf=None):
-    """pixel_nerf_yolo_b200 PixelNeRFNet with synthetic weights and an injected (synthetic) encoder output."""
+def build_net(scene, device="cuda", coarse_seed=1, fine_seed=2, precision="bf16", model_conf=None, train=False):
+    """pixel_nerf_yolo_b200 PixelNeRFNet with synthetic weights and an injected (synthetic) encoder output.
+    ``train=False`` freezes the parameters (an inference build: the drop-in, like the reference, records a backward pass
+    whenever gradient mode is on and something on the path requires grad, whatever the train/eval mode)."""
     from pixel_nerf_yolo_b200.model import make_model
     net = make_model(ConfigTree.from_dict(model_conf or MODEL_CONF)).eval()
     C = scene["latent"].shape[1]
@@ -34,6 +36,10 @@ def build_net(scene, device="cuda", coarse_seed=1, fine_seed=2, precision="bf16"
     net.encoder.set_latent(scene["latent"].to(device))
     net.set_cameras(poses.reshape(-1, 4, 4).to(device), scene["focal"].to(device), scene["image_wh"])
     net.precision = precision
+    if train:
+        net.train()
+    else:
+        net.requires_grad_(False)
     return net
 
 

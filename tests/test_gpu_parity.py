@@ -175,8 +175,7 @@ def test_gather_encode_matches_oracle(lib):
     for fp32 in (True, False):
         sc, keep = net._scene(fp32_maps=fp32)
         xd, dd = xyz.cuda(), dirs.cuda()
-        pts = _lib.Points()
-        pts.xyz, pts.dirs, pts.mode, pts.P = xd.data_ptr(), dd.data_ptr(), 0, P
+        pts = _lib.points_xyz(xd, dd)
         lat = torch.empty(2 * 3 * P, 512, device="cuda", dtype=torch.float32)
         zf = torch.empty(2 * 3 * P, 42, device="cuda")
         _lib.check(lib.pnr_gather_encode(sc, pts, lat.data_ptr(), zf.data_ptr(), 1, 6, 1.5, _lib.stream_ptr(lat.device)), "gather")

@@ -44,7 +44,7 @@ def _renderer(**kw):
 
 
 def _train_net(scene):
-    net = H.build_net(scene, precision="bf16").train()
+    net = H.build_net(scene, precision="bf16", train=True)
     lat = scene["latent"].cuda().clone().requires_grad_(True)
     net.encoder.set_latent(lat)
     return net, lat

@@ -57,7 +57,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pnr_version() == 2
+    assert lib.pnr_version() == 3
     # struct layouts agree with the header (sizes computed by the C compiler)
     src = '#include "pixelnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu",sizeof(pnr_scene),sizeof(pnr_points),sizeof(pnr_mlp_params),sizeof(pnr_mlp_grads),sizeof(pnr_render_args));}'
     exe = os.path.join(ROOT, "pixel-nerf-yolo_b200", "csrc", "build", "sizes")
@@ -190,3 +190,51 @@ def test_state_dict_is_checkpoint_compatible_with_reference():
     import torch
     fake = {k: torch.zeros(shape, dtype=getattr(torch, dt.split(".")[1])) for k, (shape, dt) in man["model"].items()}
     net.load_state_dict(fake, strict=True)
+
+
+def test_render_state_key_tracks_generations():
+    """MultiDeviceRenderer / the prepared render arguments decide "did anything change" from explicit generation counters
+    (a new encode, new cameras, new weights), never from pointer identity, which the caching allocator re-issues (ABA)."""
+    from pixel_nerf_yolo_b200.conf import ConfigTree
+    from pixel_nerf_yolo_b200.dist import MultiDeviceRenderer
+    from pixel_nerf_yolo_b200.model import make_model
+    from pixel_nerf_yolo_b200.render import NeRFRenderer
+    import pixel_nerf_yolo_b200.synth as synth
+    conf = {"use_encoder": True, "use_xyz": True, "use_code": True, "code": {"num_freqs": 6, "freq_factor": 1.5, "include_input": True},
+            "use_viewdirs": True, "use_code_viewdirs": False,
+            "mlp_coarse": {"type": "resnet", "n_blocks": 5, "d_hidden": 512, "d_out": 4, "combine_layer": 3, "combine_type": "average"},
+            "mlp_fine": {"type": "resnet", "n_blocks": 5, "d_hidden": 512, "d_out": 4, "combine_layer": 3, "combine_type": "average"},
+            "encoder": {"backbone": "resnet34", "pretrained": False, "num_layers": 4, "index_padding": "zeros"}}
+    net = make_model(ConfigTree.from_dict(conf)).eval()
+    scene = synth.scene_config1(seed=1, num_views=3, feat=8)
+    net.num_objs, net.num_views_per_obj = 1, 3
+    net.encoder.set_latent(scene["latent"])
+    net.set_cameras(scene["poses"].reshape(-1, 4, 4), scene["focal"], scene["image_wh"])
+    md = MultiDeviceRenderer(NeRFRenderer(64, 32, 16).bind_parallel(net, None, simple_output=True), [0, 1])
+    k0 = md.state_key()
+    assert md.state_key() == k0
+    # same storage, same version, new content: pointer identity would not notice a re-encode into a recycled buffer
+    lat = scene["latent"]
+    net.encoder.set_latent(lat)
+    k1 = md.state_key()
+    assert k1 != k0
+    net.set_cameras(scene["poses"].reshape(-1, 4, 4), scene["focal"], scene["image_wh"])
+    k2 = md.state_key()
+    assert k2 != k1
+    with torch.no_grad():
+        net.mlp_coarse.lin_in.bias.add_(1.0)                      # optimizer-style in-place step
+    k3 = md.state_key()
+    assert k3 != k2
+    net.mlp_fine.lin_out.weight.data.mul_(2.0)                    # behind autograd's back: explicit invalidate()
+    assert md.state_key() == k3
+    net.mlp_fine.invalidate()
+    k4 = md.state_key()
+    assert k4 != k3
+    net.mlp_coarse.load_state_dict(synth.mlp_state(3))
+    assert md.state_key() != k4
+    md._key = md.state_key()
+    md.invalidate()
+    assert md._key is None
+    # a call that would record a backward pass is refused (the replicas' gradients are not reduced onto `net`)
+    with pytest.raises(NotImplementedError, match="inference driver"):
+        md(torch.zeros(1, 4, 8))
