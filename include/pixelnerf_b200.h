@@ -71,6 +71,10 @@ typedef struct pnr_scene {
  * (10-bit mantissa) and fp32 accumulation instead of fp32 SIMT arithmetic: ~3x faster, gradients within ~5e-3 of autograd
  * instead of ~1e-4. */
 #define PNR_SCENE_TRAIN_TF32 8
+/* Training path only: the tcgen05 path -- bf16 operands (activations kept on a bf16 tape, 1 KiB per row and layer), fp32
+ * accumulation in TMEM, cta_group::2 GEMMs for the forward layers, the input gradients and the weight gradients
+ * (csrc/train_umma.cu).  Gradients within ~2e-2 of autograd (bf16 operand rounding).  d_hidden = 512, C a multiple of 64. */
+#define PNR_SCENE_TRAIN_BF16 16
 
 /* Where the query points of a field evaluation come from. */
 typedef struct pnr_points {
@@ -115,6 +119,10 @@ int pnr_sample_fine(const float* weights, const float* depth, const float* rays,
 /* YoloRenderer.forward's per-ray reduction (src/render/yolo.py:96-114): raw field values out (B, K, A*7) ->
  * result (B, A, 7) = [max_k p, sum_k(v p) / (sum_k p + 1e-5)], p = sigmoid(first value of the anchor). */
 int pnr_yolo_reduce(const float* out, float* result, int B, int K, int num_anchors, void* stream);
+
+/* Backward of pnr_yolo_reduce (what autograd derives for yolo.py:96-114; torch.max sends its gradient to the first maximal
+ * sample): out (B, K, A*7) raw field values, d_result (B, A, 7) -> d_out (B, K, A*7), overwritten. */
+int pnr_yolo_reduce_backward(const float* out, const float* d_result, float* d_out, int B, int K, int num_anchors, void* stream);
 
 /* ---- encode-side repack (SpatialEncoder.latent NCHW fp32 -> channels-last) ---------------------- */
 /* src (N, C, H, W) fp32 -> dst (N, H, W, C) bf16 (to_fp32=0) or fp32 (to_fp32=1). */

@@ -422,9 +422,10 @@ def gen_rays_yolo(poses_w2c: torch.Tensor, width: int, height: int, focal, c, z_
 
 
 def yolo_render(scene: Scene, mlp: Dict[str, torch.Tensor], rays: torch.Tensor, noise: torch.Tensor, *,
-                n_coarse: int = 128, num_anchors: int = 3, **field_kw) -> torch.Tensor:
-    """YoloRenderer.forward (src/render/yolo.py:37-114).  rays (B, 8), noise (B, Kc) -> (B, anchors, 7)."""
-    with torch.no_grad():
+                n_coarse: int = 128, num_anchors: int = 3, grad: bool = False, **field_kw) -> torch.Tensor:
+    """YoloRenderer.forward (src/render/yolo.py:37-114).  rays (B, 8), noise (B, Kc) -> (B, anchors, 7).  ``grad=True`` records
+    the autograd graph the reference's YoloTrainer back-propagates through (train/trainlib/YoloTrainer.py:140-190)."""
+    with torch.set_grad_enabled(grad):
         r = rays.reshape(-1, 8)
         z = sample_coarse(r, noise, n_coarse, False)                        # yolo.py:15-27
         B, K = z.shape

@@ -21,12 +21,13 @@ SCENE_MASK_NONNEG_Z = 1
 SCENE_RAW_OUTPUT = 2
 SCENE_PROJECTED = 4
 SCENE_TRAIN_TF32 = 8
+SCENE_TRAIN_BF16 = 16
 
 # every symbol include/pixelnerf_b200.h declares
 EXPORTS = [
     "pnr_version", "pnr_last_error", "pnr_device_supported", "pnr_sample_coarse", "pnr_composite",
     "pnr_sample_fine", "pnr_pack_features", "pnr_gather_encode", "pnr_mlp_pack_bytes", "pnr_mlp_pack",
-    "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_gen_rays_yolo",
+    "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_gen_rays_yolo", "pnr_yolo_reduce_backward",
     "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
     "pnr_field_tape_bytes", "pnr_field_forward_train", "pnr_field_backward_workspace_bytes", "pnr_field_backward",
     "pnr_composite_backward", "pnr_sample_fine_depth_backward", "pnr_pyramid_pack", "pnr_gen_rays", "pnr_yolo_reduce", "pnr_image_output", "pnr_rgb_loss",
@@ -34,7 +35,8 @@ EXPORTS = [
     "pnr_render_workspace_bytes", "pnr_render_forward",
 ]
 # lab equipment (csrc/pnr_lab.h, internal): micro-benchmarks and the tcgen05 self test; not part of the product ABI
-LAB_EXPORTS = ["pnr_umma_selftest", "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench"]
+LAB_EXPORTS = ["pnr_umma_selftest", "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_dsmem_bench",
+               "pnr_lab_gemm_workspace_bytes", "pnr_lab_rowgemm", "pnr_lab_wgrad"]
 ABI_VERSION = 3
 
 
@@ -145,6 +147,10 @@ def load() -> C.CDLL:
     lib.pnr_ingest_bench_tma.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.pnr_umma_bench.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp]
     lib.pnr_dsmem_bench.argtypes = [i32, i32, i32, i32, vp, vp]
+    lib.pnr_lab_gemm_workspace_bytes.argtypes = [C.c_longlong, i32, i32]
+    lib.pnr_lab_gemm_workspace_bytes.restype = C.c_size_t
+    lib.pnr_lab_rowgemm.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_longlong, i32, i32, i32, vp, C.c_size_t, vp]
+    lib.pnr_lab_wgrad.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, vp, C.c_size_t, vp]
     lib.pnr_field_tape_bytes.argtypes = [C.POINTER(Scene), C.POINTER(Points), C.POINTER(MlpParams)]
     lib.pnr_field_tape_bytes.restype = C.c_size_t
     lib.pnr_field_forward_train.argtypes = [C.POINTER(Scene), C.POINTER(Points), C.POINTER(MlpParams), vp, vp,
@@ -167,6 +173,7 @@ def load() -> C.CDLL:
     lib.pnr_image_output.argtypes = [vp, vp, vp, vp, C.c_longlong, f32, f32, vp]
     lib.pnr_rgb_loss.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp]
     lib.pnr_yolo_reduce.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.pnr_yolo_reduce_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.pnr_gen_rays.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, f32, f32, f32, f32, f32, f32, vp]
     lib.pnr_gen_rays_yolo.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp]
     for name in EXPORTS + LAB_EXPORTS:

@@ -9,6 +9,7 @@
 // explicit chain of kernels here.  Arithmetic is fp32 on the CUDA cores (SIMT SGEMM in all four operand layouts):
 // the training step is the parity case of this round (gradients vs autograd <= 1e-3 relative), not the timed one.
 #include "pnr_common.cuh"
+#include "train_umma.cuh"
 
 namespace pnr {
 
@@ -395,28 +396,79 @@ __global__ void view_mean_bwd_kernel(const float* __restrict__ dy, float* __rest
   dx[i] = dy[((long long)s * P + p) * H + h] / (float)NS;
 }
 
-// lin_out (H -> d_out <= 8) on relu(x), sigmoid(rgb) / relu(sigma)          resnetfc.py:185, models.py:312-317
-__global__ void lin_out_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                                   float* __restrict__ out, long long rows, int H, int d_out) {
+// bf16 path helpers -----------------------------------------------------------------------------------------------------
+// view mean that also emits the relu'd bf16 operand of the next fc_0
+__global__ void view_mean_bf16_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ y16, int SB, int NS,
+                                      int P, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)SB * P * H) return;
+  const int h = (int)(i % H);
+  const long long sp = i / H;
+  const int p = (int)(sp % P), s = (int)(sp / P);
+  float acc = 0.f;
+  for (int v = 0; v < NS; ++v) acc += x[(((long long)s * NS + v) * P + p) * H + h];
+  const float m = acc / (float)NS;
+  y[i] = m;
+  y16[i] = __float2bfloat16_rn(fmaxf(m, 0.f));
+}
+__global__ void view_mean_bwd_bf16_kernel(const float* __restrict__ dy, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int SB,
+                                          int NS, int P, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)SB * NS * P * H) return;
+  const int h = (int)(i % H);
+  const long long svp = i / H;
+  const int p = (int)(svp % P);
+  const int s = (int)(svp / P / NS);
+  const float g = dy[((long long)s * P + p) * H + h] / (float)NS;
+  dx[i] = g;
+  dx16[i] = __float2bfloat16_rn(g);
+}
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dY, float* __restrict__ db, long long M, int N, int rows_per_block) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += __bfloat162float(dY[r * N + j]);
+    atomicAdd(db + j, acc);
+  }
+}
+// z-features (rows, d_in) fp32 -> (rows, 64) bf16, zero padded: the K = 64 operand of lin_in
+__global__ void zf_pad_bf16_kernel(const float* __restrict__ zf, __nv_bfloat16* __restrict__ out, long long rows, int d_in) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 64) return;
+  const long long r = i >> 6;
+  const int c = (int)(i & 63);
+  out[i] = __float2bfloat16_rn(c < d_in ? zf[r * d_in + c] : 0.f);
+}
+
+// lin_out (H -> d_out <= 32) on relu(x): sigmoid(rgb) / relu(sigma) (resnetfc.py:185, models.py:312-317), or the raw values
+// (YOLO head, models.py:309-310).  T = float (the fp32 tape holds x) or __nv_bfloat16 (the bf16 tape holds relu(x)).
+__device__ __forceinline__ float ld_act(const float* p) { return *p; }
+__device__ __forceinline__ float ld_act(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__global__ void lin_out_fwd_kernel(const T* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                   float* __restrict__ out, long long rows, int H, int d_out, int raw) {
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
   for (int o = 0; o < d_out; ++o) {
     float acc = 0.f;
-    for (int k = lane; k < H; k += 32) acc = fmaf(fmaxf(x[row * H + k], 0.f), W[o * H + k], acc);
+    for (int k = lane; k < H; k += 32) acc = fmaf(fmaxf(ld_act(x + row * H + k), 0.f), W[o * H + k], acc);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     if (lane == 0) {
       float v = acc + bias[o];
-      out[row * d_out + o] = (o < 3) ? 1.0f / (1.0f + expf(-v)) : fmaxf(v, 0.f);
+      out[row * d_out + o] = raw ? v : ((o < 3) ? 1.0f / (1.0f + expf(-v)) : fmaxf(v, 0.f));
     }
   }
 }
 // One warp per point: d_raw = d_out * act'(out); dx = (d_raw W) * (x > 0); per-block partial dW / db -> atomics.
+// dx (fp32) and, optionally, a bf16 copy dx16 (operand of the tcgen05 GEMMs).
+template <typename T>
 __global__ void __launch_bounds__(256)
-lin_out_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ out,
-                   const float* __restrict__ d_out_act, float* __restrict__ dx, float* __restrict__ dW,
-                   float* __restrict__ db, long long rows, int H, int d_out, int rows_per_warp) {
+lin_out_bwd_kernel(const T* __restrict__ x, const float* __restrict__ W, const float* __restrict__ out,
+                   const float* __restrict__ d_out_act, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
+                   float* __restrict__ dW, float* __restrict__ db, long long rows, int H, int d_out, int rows_per_warp, int raw) {
   extern __shared__ float sm[];                 // [d_out][H] partial dW of this block, then [d_out] partial db
   float* sW = sm;
   float* sb = sm + d_out * H;
@@ -427,21 +479,23 @@ lin_out_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W, con
   for (int rr = 0; rr < rows_per_warp; ++rr) {
     const long long row = warp * rows_per_warp + rr;
     if (row >= rows) break;
-    float draw[8];
+    float draw[32];
     for (int o = 0; o < d_out; ++o) {
       const float y = out[row * d_out + o], gy = d_out_act[row * d_out + o];
-      draw[o] = (o < 3) ? gy * y * (1.0f - y) : (y > 0.f ? gy : 0.f);     // sigmoid' = y (1 - y); relu' = [y > 0]
+      draw[o] = raw ? gy : ((o < 3) ? gy * y * (1.0f - y) : (y > 0.f ? gy : 0.f));     // sigmoid' = y (1 - y); relu' = [y > 0]
     }
     if (lane == 0) for (int o = 0; o < d_out; ++o) atomicAdd(sb + o, draw[o]);
     for (int k = lane; k < H; k += 32) {
-      const float xv = x[row * H + k];
+      const float xv = ld_act(x + row * H + k);
       const float r = fmaxf(xv, 0.f);
       float g = 0.f;
       for (int o = 0; o < d_out; ++o) {
         g = fmaf(draw[o], W[o * H + k], g);
         atomicAdd(sW + o * H + k, draw[o] * r);
       }
-      dx[row * H + k] = xv > 0.f ? g : 0.f;
+      g = xv > 0.f ? g : 0.f;
+      dx[row * H + k] = g;
+      if (dx16) dx16[row * H + k] = __float2bfloat16_rn(g);
     }
   }
   __syncthreads();
@@ -583,16 +637,232 @@ static int check_train(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   if (rc) return rc;
   PNR_REQUIRE(mp, PNR_ERR_ARG, "%s: null params", who);
   PNR_REQUIRE(sc->feat_fp32, PNR_ERR_ARG, "%s: the training path reads fp32 channels-last feature maps", who);
-  PNR_REQUIRE((sc->flags & ~PNR_SCENE_TRAIN_TF32) == 0, PNR_ERR_UNSUPPORTED, "%s: the YOLO / projected modes (scene flags %d) have no training path yet", who, sc->flags);
+  PNR_REQUIRE((sc->flags & PNR_SCENE_PROJECTED) == 0, PNR_ERR_UNSUPPORTED, "%s: pre-projected feature maps (PNR_SCENE_PROJECTED) have no training path: the projection depends on the weights being trained", who);
+  PNR_REQUIRE(!((sc->flags & PNR_SCENE_TRAIN_TF32) && (sc->flags & PNR_SCENE_TRAIN_BF16)), PNR_ERR_ARG, "%s: choose one of PNR_SCENE_TRAIN_TF32 / PNR_SCENE_TRAIN_BF16", who);
   g_use_tf32 = (sc->flags & PNR_SCENE_TRAIN_TF32) ? 1 : 0;
+  if (sc->flags & PNR_SCENE_TRAIN_BF16) {
+    PNR_REQUIRE(mp->d_hidden == kHidden && sc->C % 64 == 0, PNR_ERR_UNSUPPORTED, "%s: the tcgen05 training path needs d_hidden = %d and C a multiple of 64 (got %d, %d)", who, kHidden, mp->d_hidden, sc->C);
+    PNR_REQUIRE(mp->d_in <= 64, PNR_ERR_UNSUPPORTED, "%s: d_in=%d > 64", who, mp->d_in);
+  }
   PNR_REQUIRE(sc->C % 4 == 0, PNR_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 4", who, sc->C);
   PNR_REQUIRE(mp->d_latent == sc->C, PNR_ERR_ARG, "%s: d_latent=%d but maps have C=%d", who, mp->d_latent, sc->C);
   PNR_REQUIRE(mp->d_in == 6 * num_freqs + 6, PNR_ERR_ARG, "%s: d_in/num_freqs mismatch", who);
   PNR_REQUIRE(mp->n_blocks >= 1 && mp->n_blocks <= 8, PNR_ERR_UNSUPPORTED, "%s: n_blocks=%d", who, mp->n_blocks);
   PNR_REQUIRE(mp->combine_layer >= 1 && mp->combine_layer <= mp->n_blocks, PNR_ERR_ARG, "%s: combine_layer=%d", who, mp->combine_layer);
   PNR_REQUIRE(mp->combine_layer < mp->n_blocks || sc->NS == 1, PNR_ERR_UNSUPPORTED, "%s: combine_layer >= n_blocks needs NS=1", who);
-  PNR_REQUIRE(mp->d_out >= 1 && mp->d_out <= 8, PNR_ERR_UNSUPPORTED, "%s: d_out=%d", who, mp->d_out);
+  PNR_REQUIRE(mp->d_out >= 1 && mp->d_out <= 32, PNR_ERR_UNSUPPORTED, "%s: d_out=%d", who, mp->d_out);
   PNR_REQUIRE((long long)sc->SB * sc->NS * q->P < (1LL << 31), PNR_ERR_ARG, "%s: too many rows per call", who);
+  return PNR_OK;
+}
+
+// ======================================================================================================================
+// tcgen05 training path (PNR_SCENE_TRAIN_BF16): bf16 operands on the tape, fp32 accumulation in TMEM (train_umma.cu).
+// The tape keeps what the backward pass needs and nothing else: the relu'd bf16 OPERAND of every layer (the weight gradient's
+// second factor; its sign pattern is the relu mask), the gathered latent and z-feature rows -- 1 KiB per row and layer instead of
+// the fp32 path's 2 x 2 KiB.  The fp32 residual stream x lives in a scratch buffer that the next block overwrites.
+struct TapeB {
+  __nv_bfloat16 *lat, *zf;          // rows x C, rows x 64
+  __nv_bfloat16* RX[9];             // rows x H: relu(x_b), operand of fc_0 of pre-combine block b
+  __nv_bfloat16* RN[8];             // rows x H: relu(fc_0 output) of pre-combine block b, operand of fc_1
+  __nv_bfloat16* RXM[9];            // pts x H: same for the post-combine blocks; RXM[n_blocks] = operand of lin_out
+  __nv_bfloat16* RNM[8];
+  float *x, *xm;                    // rows x H, pts x H fp32 residual stream (scratch of the forward pass)
+  uint8_t* wpack;                   // forward packed weights
+  size_t bytes;
+};
+struct WPack { size_t lin_in, linz[8], fc0[8], fc1[8], total; };
+static WPack wpack_layout(int C, int d_in_pad, int H, int nb, int CL, bool transposed) {
+  // forward: out = H, in = K.  transposed (input gradients): out = K (lin_z: C, lin_in: d_in_pad), in = H.
+  WPack w = {};
+  size_t off = 0;
+  auto take = [&](int n_out, int n_in) { size_t o = off; off += (tg::packed_rowgemm_bytes(n_out, n_in) + 1023) & ~(size_t)1023; return o; };
+  w.lin_in = transposed ? take(d_in_pad, H) : take(H, d_in_pad);
+  for (int b = 0; b < CL; ++b) w.linz[b] = transposed ? take(C, H) : take(H, C);
+  for (int b = 0; b < nb; ++b) { w.fc0[b] = take(H, H); w.fc1[b] = take(H, H); }
+  w.total = off;
+  return w;
+}
+static TapeB carve_tape_b(uint8_t* base, long long rows, long long pts, int C, int H, int nb, int CL) {
+  TapeB t = {};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += (bytes + 1023) & ~(size_t)1023; return p; };
+  t.lat = (__nv_bfloat16*)take((size_t)rows * C * 2);
+  t.zf = (__nv_bfloat16*)take((size_t)rows * 64 * 2);
+  for (int b = 0; b < CL; ++b) t.RX[b] = (__nv_bfloat16*)take((size_t)rows * H * 2);
+  for (int b = 0; b < CL; ++b) t.RN[b] = (__nv_bfloat16*)take((size_t)rows * H * 2);
+  for (int b = CL; b <= nb; ++b) t.RXM[b] = (__nv_bfloat16*)take((size_t)pts * H * 2);
+  for (int b = CL; b < nb; ++b) t.RNM[b] = (__nv_bfloat16*)take((size_t)pts * H * 2);
+  t.x = (float*)take((size_t)rows * H * 4);
+  t.xm = (float*)take((size_t)pts * H * 4);
+  t.wpack = take(wpack_layout(C, 64, H, nb, CL, false).total);
+  t.bytes = off + 1024;
+  return t;
+}
+static uint8_t* align1k(void* p) { return (uint8_t*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023); }
+
+static int pack_all(const pnr_mlp_params* mp, int C, bool transposed, uint8_t* dst, const WPack& w, cudaStream_t st, int* launches) {
+  const int H = mp->d_hidden, nb = mp->n_blocks, CL = mp->combine_layer;
+  int rc;
+#define PK(W, rows, cols, off) do { if ((rc = tg::pack_rowgemm(W, rows, cols, cols, transposed ? 1 : 0, dst + (off), st))) return rc; ++*launches; } while (0)
+  PK(mp->lin_in_w, H, mp->d_in, w.lin_in);
+  for (int b = 0; b < CL; ++b) PK(mp->linz_w[b], H, C, w.linz[b]);
+  for (int b = 0; b < nb; ++b) { PK(mp->fc0_w[b], H, H, w.fc0[b]); PK(mp->fc1_w[b], H, H, w.fc1[b]); }
+#undef PK
+  return PNR_OK;
+}
+
+// y = epilogue(A0 W0^T [+ A1 W1^T]) with the common argument patterns of the chain
+static int rg(const __nv_bfloat16* A0, long long lda0, int K0, const void* W0, const __nv_bfloat16* A1, long long lda1, int K1, const void* W1,
+              tg::RowGemmArgs g, cudaStream_t st, int* launches) {
+  tg::RowGemmSrc s0 = {A0, lda0, K0, W0}, s1 = {A1, lda1, K1, W1};
+  int rc = tg::rowgemm(s0, A1 ? &s1 : nullptr, g, st);
+  if (rc) return rc;
+  ++*launches;
+  return PNR_OK;
+}
+
+static int forward_bf16(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, float* out, void* tape, int num_freqs,
+                        float freq_factor, cudaStream_t st) {
+  const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
+  const int H = mp->d_hidden, C = sc->C, d_in = mp->d_in, nb = mp->n_blocks, CL = mp->combine_layer;
+  const TapeB t = carve_tape_b(align1k(tape), rows, pts, C, H, nb, CL);
+  const WPack w = wpack_layout(C, 64, H, nb, CL, false);
+  int launches = 0, rc;
+  // gather: latent rows straight to bf16; z-features via an fp32 scratch (the x buffer, not yet in use) then padded to K = 64
+  float* zf32 = t.x;
+  rc = pnr_gather_encode(sc, q, t.lat, zf32, 0, num_freqs, freq_factor, (void*)st);
+  if (rc) return rc;
+  ++launches;
+  zf_pad_bf16_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, st>>>(zf32, t.zf, rows, d_in);
+  PNR_CHECK_LAUNCH("bwd::zf_pad_bf16_kernel");
+  ++launches;
+  if ((rc = pack_all(mp, C, false, t.wpack, w, st, &launches))) return rc;
+  tg::RowGemmArgs g;
+  auto base = [&](long long M) { tg::RowGemmArgs a = {}; a.M = M; a.n_valid = H; return a; };
+  // x_0 = lin_in(zf) + lin_z[0](z)                                             resnetfc.py:149,176-180
+  g = base(rows); g.bias = mp->lin_in_b; g.bias2 = mp->linz_b[0]; g.out_f32 = t.x; g.ld_f32 = H; g.out_bf16 = t.RX[0]; g.ld_bf16 = H; g.relu_out = 1;
+  if ((rc = rg(t.zf, 64, 64, t.wpack + w.lin_in, t.lat, C, C, t.wpack + w.linz[0], g, st, &launches))) return rc;
+  for (int b = 0; b < CL; ++b) {
+    g = base(rows); g.bias = mp->fc0_b[b]; g.out_bf16 = t.RN[b]; g.ld_bf16 = H; g.relu_out = 1;                       // net = fc_0(relu(x))
+    if ((rc = rg(t.RX[b], H, H, t.wpack + w.fc0[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
+    const bool more = b + 1 < CL;                                                                                      // x += fc_1(relu(net)) [+ lin_z[b+1](z)]
+    g = base(rows); g.bias = mp->fc1_b[b]; g.bias2 = more ? mp->linz_b[b + 1] : nullptr; g.res_in = t.x; g.ld_res = H; g.out_f32 = t.x; g.ld_f32 = H;
+    if (more) { g.out_bf16 = t.RX[b + 1]; g.ld_bf16 = H; g.relu_out = 1; }
+    if ((rc = rg(t.RN[b], H, H, t.wpack + w.fc1[b], more ? t.lat : nullptr, C, C, more ? t.wpack + w.linz[b + 1] : nullptr, g, st, &launches))) return rc;
+  }
+  {
+    const long long n = pts * H;
+    view_mean_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.x, t.xm, t.RXM[CL], sc->SB, sc->NS, q->P, H);      // util.py:489-499
+    PNR_CHECK_LAUNCH("bwd::view_mean_bf16_kernel");
+    ++launches;
+  }
+  for (int b = CL; b < nb; ++b) {
+    g = base(pts); g.bias = mp->fc0_b[b]; g.out_bf16 = t.RNM[b]; g.ld_bf16 = H; g.relu_out = 1;
+    if ((rc = rg(t.RXM[b], H, H, t.wpack + w.fc0[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
+    g = base(pts); g.bias = mp->fc1_b[b]; g.res_in = t.xm; g.ld_res = H; g.out_f32 = t.xm; g.ld_f32 = H; g.out_bf16 = t.RXM[b + 1]; g.ld_bf16 = H; g.relu_out = 1;
+    if ((rc = rg(t.RNM[b], H, H, t.wpack + w.fc1[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
+  }
+  lin_out_fwd_kernel<__nv_bfloat16><<<(unsigned)((pts * 32 + 255) / 256), 256, 0, st>>>(t.RXM[nb], mp->lin_out_w, mp->lin_out_b, out, pts, H, mp->d_out,
+                                                                                         (sc->flags & PNR_SCENE_RAW_OUTPUT) ? 1 : 0);
+  PNR_CHECK_LAUNCH("bwd::lin_out_fwd_kernel");
+  ++launches;
+  reset_launch_count();
+  count_launch(launches);
+  return PNR_OK;
+}
+
+struct BwdWsB { float *dx, *dxm, *dlat, *dzf; __nv_bfloat16 *dx16, *dn16; uint8_t* wpack; size_t bytes; };
+static BwdWsB carve_bwd_b(uint8_t* base, long long rows, long long pts, int C, int d_in, int H, int nb, int CL) {
+  BwdWsB b = {};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += (bytes + 1023) & ~(size_t)1023; return p; };
+  b.dx = (float*)take((size_t)rows * H * 4);
+  b.dxm = (float*)take((size_t)pts * H * 4);
+  b.dlat = (float*)take((size_t)rows * C * 4);
+  b.dzf = (float*)take((size_t)rows * d_in * 4);
+  b.dx16 = (__nv_bfloat16*)take((size_t)rows * H * 2);
+  b.dn16 = (__nv_bfloat16*)take((size_t)rows * H * 2);
+  b.wpack = take(wpack_layout(C, 64, H, nb, CL, true).total);
+  b.bytes = off + 1024;
+  return b;
+}
+
+static int backward_bf16(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp, const void* tape, const float* out,
+                         const float* d_out, const pnr_mlp_grads* gr, float* d_feat, float* d_xyz, float* d_z, void* workspace,
+                         int num_freqs, float freq_factor, cudaStream_t st) {
+  const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
+  const int H = mp->d_hidden, C = sc->C, d_in = mp->d_in, nb = mp->n_blocks, CL = mp->combine_layer, NS = sc->NS;
+  const TapeB t = carve_tape_b(align1k(const_cast<void*>(tape)), rows, pts, C, H, nb, CL);
+  const BwdWsB ws = carve_bwd_b(align1k(workspace), rows, pts, C, d_in, H, nb, CL);
+  const WPack w = wpack_layout(C, 64, H, nb, CL, true);
+  int launches = 0, rc;
+  if ((rc = pack_all(mp, C, true, ws.wpack, w, st, &launches))) return rc;
+  const int raw = (sc->flags & PNR_SCENE_RAW_OUTPUT) ? 1 : 0;
+  {
+    const int rpw = 4;
+    const long long warps = (pts + rpw - 1) / rpw;
+    const size_t smem = (size_t)(mp->d_out * H + mp->d_out) * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(lin_out_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lin_out_bwd_kernel<__nv_bfloat16><<<(unsigned)((warps * 32 + 255) / 256), 256, smem, st>>>(
+        t.RXM[nb], mp->lin_out_w, out, d_out, ws.dxm, ws.dx16, gr->lin_out_w, gr->lin_out_b, pts, H, mp->d_out, rpw, raw);
+    PNR_CHECK_LAUNCH("bwd::lin_out_bwd_kernel");
+    ++launches;
+  }
+#define STEP(call) do { rc = (call); if (rc) return rc; ++launches; } while (0)
+  auto colsum16 = [&](const __nv_bfloat16* dY, float* db, long long M) -> int {
+    const int rpb = 256;
+    colsum_bf16_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(dY, db, M, H, rpb);
+    PNR_CHECK_LAUNCH("bwd::colsum_bf16_kernel");
+    return PNR_OK;
+  };
+  // one residual block backwards (resnetfc.py:53-62); dx (fp32 master + bf16 operand copy) is updated in place
+  auto block_bwd = [&](const __nv_bfloat16* RXb, const __nv_bfloat16* RNb, int b, float* dx, long long M) -> int {
+    STEP(tg::wgrad(ws.dx16, H, RNb, H, gr->fc1_w[b], H, M, H, H, st));                          // dW1 += dx^T relu(net)
+    STEP(colsum(dx, gr->fc1_b[b], M, H, st));
+    tg::RowGemmArgs g = {};                                                                      // dnet = (dx W1) * [net > 0]
+    g.M = M; g.n_valid = H; g.mask_src = RNb; g.ld_mask = H; g.out_bf16 = ws.dn16; g.ld_bf16 = H;
+    if ((rc = rg(ws.dx16, H, H, ws.wpack + w.fc1[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
+    STEP(tg::wgrad(ws.dn16, H, RXb, H, gr->fc0_w[b], H, M, H, H, st));                          // dW0 += dnet^T relu(x)
+    STEP(colsum16(ws.dn16, gr->fc0_b[b], M));
+    g = {};                                                                                      // dx += (dnet W0) * [x > 0]
+    g.M = M; g.n_valid = H; g.mask_src = RXb; g.ld_mask = H; g.res_in = dx; g.ld_res = H; g.out_f32 = dx; g.ld_f32 = H; g.out_bf16 = ws.dx16; g.ld_bf16 = H;
+    if ((rc = rg(ws.dn16, H, H, ws.wpack + w.fc0[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
+    return PNR_OK;
+  };
+  for (int b = nb - 1; b >= CL; --b)
+    if ((rc = block_bwd(t.RXM[b], t.RNM[b], b, ws.dxm, pts))) return rc;
+  {
+    const long long n = rows * H;
+    view_mean_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.dxm, ws.dx, ws.dx16, sc->SB, NS, q->P, H);
+    PNR_CHECK_LAUNCH("bwd::view_mean_bwd_bf16_kernel");
+    ++launches;
+  }
+  for (int b = CL - 1; b >= 0; --b) {
+    if ((rc = block_bwd(t.RX[b], t.RN[b], b, ws.dx, rows))) return rc;
+    STEP(tg::wgrad(ws.dx16, H, t.lat, C, gr->linz_w[b], C, rows, H, C, st));                     // x += lin_z[b](z): resnetfc.py:176-182
+    STEP(colsum(ws.dx, gr->linz_b[b], rows, H, st));
+    if (d_feat || d_xyz || d_z) {
+      tg::RowGemmArgs g = {};                                                                    // dlat (+)= dx Wz_b
+      g.M = rows; g.n_valid = C; g.out_f32 = ws.dlat; g.ld_f32 = C;
+      if (b != CL - 1) { g.res_in = ws.dlat; g.ld_res = C; }
+      if ((rc = rg(ws.dx16, H, H, ws.wpack + w.linz[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
+    }
+  }
+  STEP(tg::wgrad(ws.dx16, H, t.zf, 64, gr->lin_in_w, d_in, rows, H, d_in, st));
+  STEP(colsum(ws.dx, gr->lin_in_b, rows, H, st));
+#undef STEP
+  if (d_feat || d_xyz || d_z) {
+    tg::RowGemmArgs g = {};                                                                      // dzf = dx W_in
+    g.M = rows; g.n_valid = d_in; g.out_f32 = ws.dzf; g.ld_f32 = d_in;
+    if ((rc = rg(ws.dx16, H, H, ws.wpack + w.lin_in, nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    gather_encode_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(*sc, *q, ws.dlat, ws.dzf, d_feat, d_xyz, d_z, num_freqs, freq_factor, rows);
+    PNR_CHECK_LAUNCH("bwd::gather_encode_bwd_kernel");
+    ++launches;
+  }
+  reset_launch_count();
+  count_launch(launches);
   return PNR_OK;
 }
 
@@ -605,6 +875,7 @@ using namespace pnr::bwd;
 extern "C" size_t pnr_field_tape_bytes(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp) {
   if (!sc || !q || !mp) return 0;
   const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
+  if (sc->flags & PNR_SCENE_TRAIN_BF16) return carve_tape_b(nullptr, rows, pts, sc->C, mp->d_hidden, mp->n_blocks, mp->combine_layer).bytes;
   return carve_tape(nullptr, rows, pts, sc->C, mp->d_in, mp->d_hidden, mp->n_blocks, mp->combine_layer).floats * sizeof(float) + 256;
 }
 
@@ -616,6 +887,7 @@ extern "C" int pnr_field_forward_train(const pnr_scene* sc, const pnr_points* q,
   PNR_REQUIRE(out && tape && tape_bytes >= pnr_field_tape_bytes(sc, q, mp), PNR_ERR_ARG, "pnr_field_forward_train: tape too small");
   const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
   if (pts == 0) return PNR_OK;
+  if (sc->flags & PNR_SCENE_TRAIN_BF16) return forward_bf16(sc, q, mp, out, tape, num_freqs, freq_factor, (cudaStream_t)stream);
   const int H = mp->d_hidden, C = sc->C, d_in = mp->d_in, nb = mp->n_blocks, CL = mp->combine_layer;
   cudaStream_t st = (cudaStream_t)stream;
   const Tape t = carve_tape((float*)tape, rows, pts, C, d_in, H, nb, CL);
@@ -640,7 +912,8 @@ extern "C" int pnr_field_forward_train(const pnr_scene* sc, const pnr_points* q,
     STEP(linear_fwd(t.XM[b], H, mp->fc0_w[b], mp->fc0_b[b], nullptr, t.NETM[b], pts, H, H, true, st));
     STEP(linear_fwd(t.NETM[b], H, mp->fc1_w[b], mp->fc1_b[b], t.XM[b], t.XM[b + 1], pts, H, H, true, st));
   }
-  lin_out_fwd_kernel<<<(unsigned)((pts * 32 + 255) / 256), 256, 0, st>>>(t.XM[nb], mp->lin_out_w, mp->lin_out_b, out, pts, H, mp->d_out);
+  lin_out_fwd_kernel<float><<<(unsigned)((pts * 32 + 255) / 256), 256, 0, st>>>(t.XM[nb], mp->lin_out_w, mp->lin_out_b, out, pts, H, mp->d_out,
+                                                                                (sc->flags & PNR_SCENE_RAW_OUTPUT) ? 1 : 0);
   PNR_CHECK_LAUNCH("bwd::lin_out_fwd_kernel");
   ++launches;
   reset_launch_count();
@@ -651,6 +924,8 @@ extern "C" int pnr_field_forward_train(const pnr_scene* sc, const pnr_points* q,
 extern "C" size_t pnr_field_backward_workspace_bytes(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_params* mp) {
   if (!sc || !q || !mp) return 0;
   const size_t rows = (size_t)sc->SB * sc->NS * q->P;
+  if (sc->flags & PNR_SCENE_TRAIN_BF16)
+    return carve_bwd_b(nullptr, (long long)rows, (long long)sc->SB * q->P, sc->C, mp->d_in, mp->d_hidden, mp->n_blocks, mp->combine_layer).bytes;
   return sizeof(float) * rows * (2 * (size_t)mp->d_hidden + (size_t)sc->C + (size_t)mp->d_in) + 256;
 }
 
@@ -668,6 +943,8 @@ extern "C" int pnr_field_backward(const pnr_scene* sc, const pnr_points* q, cons
               "pnr_field_backward: d_xyz goes with explicit points (mode 0), d_z with rays x depths (mode 1)");
   const long long rows = (long long)sc->SB * sc->NS * q->P, pts = (long long)sc->SB * q->P;
   if (pts == 0) return PNR_OK;
+  if (sc->flags & PNR_SCENE_TRAIN_BF16)
+    return backward_bf16(sc, q, mp, tape, out, d_out, gr, d_feat, d_xyz, d_z, workspace, num_freqs, freq_factor, (cudaStream_t)stream);
   const int H = mp->d_hidden, C = sc->C, d_in = mp->d_in, nb = mp->n_blocks, CL = mp->combine_layer, NS = sc->NS;
   cudaStream_t st = (cudaStream_t)stream;
   const Tape t = carve_tape((float*)const_cast<void*>(tape), rows, pts, C, d_in, H, nb, CL);
@@ -680,8 +957,10 @@ extern "C" int pnr_field_backward(const pnr_scene* sc, const pnr_points* q, cons
     const int rpw = 4;
     const long long warps = (pts + rpw - 1) / rpw;
     const size_t smem = (size_t)(mp->d_out * H + mp->d_out) * sizeof(float);
-    lin_out_bwd_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, smem, st>>>(t.XM[nb], mp->lin_out_w, out, d_out, dA,
-                                                                                gr->lin_out_w, gr->lin_out_b, pts, H, mp->d_out, rpw);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(lin_out_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lin_out_bwd_kernel<float><<<(unsigned)((warps * 32 + 255) / 256), 256, smem, st>>>(t.XM[nb], mp->lin_out_w, out, d_out, dA, nullptr,
+                                                                                       gr->lin_out_w, gr->lin_out_b, pts, H, mp->d_out, rpw,
+                                                                                       (sc->flags & PNR_SCENE_RAW_OUTPUT) ? 1 : 0);
     PNR_CHECK_LAUNCH("bwd::lin_out_bwd_kernel");
     ++launches;
   }

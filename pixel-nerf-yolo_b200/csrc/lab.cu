@@ -379,3 +379,61 @@ extern "C" int pnr_dsmem_bench(int mode, int bytes, int iters, int warps, long l
   return PNR_OK;
 }
 
+
+// ---- stand-alone entry points of the tcgen05 training GEMMs (train_umma.cu), for tests/test_gpu_train.py ---------------------
+#include "train_umma.cuh"
+namespace pnr {
+__global__ void lab_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int cols, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const long long r = i / ld;
+  const int c = (int)(i - r * ld);
+  dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+}
+}  // namespace pnr
+
+extern "C" size_t pnr_lab_gemm_workspace_bytes(long long M, int N, int K) {
+  const size_t ldk = (size_t)((K + 63) / 64 * 64), ldn = (size_t)((N + 63) / 64 * 64);
+  return (size_t)M * ldk * 2 + (size_t)M * ldn * 2 + pnr::tg::packed_rowgemm_bytes(N, K) + 4096;
+}
+
+// out[M, N] = epilogue(A[M, K] W[N, K]^T): A, W fp32 device inputs rounded to bf16; optional bias [N], mask_src [M, N] (fp32,
+// rounded to bf16), res_in [M, N]; out_f32 and / or out_bf16_as_f32 ([M, N] fp32 copy of the bf16 output) may be null.
+extern "C" int pnr_lab_rowgemm(const float* A, const float* W, const float* bias, const float* mask_src, const float* res_in,
+                               float* out_f32, void* out_bf16, long long M, int N, int K, int relu_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  using namespace pnr;
+  reset_launch_count();
+  PNR_REQUIRE(A && W && workspace && workspace_bytes >= pnr_lab_gemm_workspace_bytes(M, N, K), PNR_ERR_ARG, "pnr_lab_rowgemm: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ldk = (K + 63) / 64 * 64, ldn = (N + 63) / 64 * 64;
+  uint8_t* p = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* A16 = (__nv_bfloat16*)p; p += ((size_t)M * ldk * 2 + 1023) & ~(size_t)1023;
+  __nv_bfloat16* M16 = (__nv_bfloat16*)p; p += ((size_t)M * ldn * 2 + 1023) & ~(size_t)1023;
+  uint8_t* Wp = p;
+  lab_to_bf16_kernel<<<(unsigned)((M * ldk + 255) / 256), 256, 0, st>>>(A, A16, M, K, ldk);
+  if (mask_src) lab_to_bf16_kernel<<<(unsigned)((M * ldn + 255) / 256), 256, 0, st>>>(mask_src, M16, M, N, ldn);
+  int rc = tg::pack_rowgemm(W, N, K, K, 0, Wp, st);
+  if (rc) return rc;
+  tg::RowGemmArgs g = {};
+  g.M = M; g.n_valid = N; g.bias = bias; g.mask_src = mask_src ? M16 : nullptr; g.ld_mask = ldn; g.res_in = res_in; g.ld_res = N;
+  g.out_f32 = out_f32; g.ld_f32 = N; g.out_bf16 = (__nv_bfloat16*)out_bf16; g.ld_bf16 = N; g.relu_out = relu_out;
+  tg::RowGemmSrc s0 = {A16, ldk, ldk, Wp};
+  return tg::rowgemm(s0, nullptr, g, st);
+}
+
+// dW[N, K] += dY[M, N]^T X[M, K] (fp32 device inputs rounded to bf16)
+extern "C" int pnr_lab_wgrad(const float* dY, const float* X, float* dW, long long M, int N, int K, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  using namespace pnr;
+  reset_launch_count();
+  PNR_REQUIRE(dY && X && dW && workspace && workspace_bytes >= pnr_lab_gemm_workspace_bytes(M, N, K), PNR_ERR_ARG, "pnr_lab_wgrad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ldk = (K + 63) / 64 * 64, ldn = (N + 63) / 64 * 64;
+  uint8_t* p = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* X16 = (__nv_bfloat16*)p; p += ((size_t)M * ldk * 2 + 1023) & ~(size_t)1023;
+  __nv_bfloat16* Y16 = (__nv_bfloat16*)p;
+  lab_to_bf16_kernel<<<(unsigned)((M * ldk + 255) / 256), 256, 0, st>>>(X, X16, M, K, ldk);
+  lab_to_bf16_kernel<<<(unsigned)((M * ldn + 255) / 256), 256, 0, st>>>(dY, Y16, M, N, ldn);
+  return tg::wgrad(Y16, ldn, X16, ldk, dW, K, M, N, K, st);
+}

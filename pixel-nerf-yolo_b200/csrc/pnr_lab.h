@@ -2,6 +2,7 @@
  * ABI (include/pixelnerf_b200.h); used by scripts/{ingest,umma,dsmem}_bench.py and tests/test_gpu_parity.py::test_umma_selftest. */
 #ifndef PNR_LAB_H
 #define PNR_LAB_H
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -21,6 +22,14 @@ int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid, long long
 /* distributed-shared-memory ping-pong of `bytes` between the two CTAs of a cluster.  mode 0: st.shared::cluster.v4 by `warps`
  * warps + proxy fence + remote arrive; mode 1: one cp.async.bulk smem->peer smem.  out[2] = cycles for `iters` transfers. */
 int pnr_dsmem_bench(int mode, int bytes, int iters, int warps, long long* out, void* stream);
+/* Stand-alone entry points of the tcgen05 training GEMMs (train_umma.cu): fp32 device inputs are rounded to bf16, then
+ * out[M,N] = epilogue(A[M,K] W[N,K]^T) (rowgemm: optional bias [N], relu mask source [M,N], residual [M,N]; fp32 and / or bf16
+ * outputs) and dW[N,K] += dY[M,N]^T X[M,K] (wgrad).  workspace: pnr_lab_gemm_workspace_bytes(M, N, K). */
+size_t pnr_lab_gemm_workspace_bytes(long long M, int N, int K);
+int pnr_lab_rowgemm(const float* A, const float* W, const float* bias, const float* mask_src, const float* res_in, float* out_f32,
+                    void* out_bf16, long long M, int N, int K, int relu_out, void* workspace, size_t workspace_bytes, void* stream);
+int pnr_lab_wgrad(const float* dY, const float* X, float* dW, long long M, int N, int K, void* workspace, size_t workspace_bytes,
+                  void* stream);
 #ifdef __cplusplus
 }
 #endif

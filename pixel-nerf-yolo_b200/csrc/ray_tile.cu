@@ -339,6 +339,61 @@ yolo_reduce_kernel(const float* __restrict__ out, float* __restrict__ res, long 
   }
 }
 
+// Backward of the reduction above (what autograd derives for src/render/yolo.py:96-114): d_res (pairs, 7) -> d_out (B, K, A*7).
+//   r_0 = max_k p_k            -> d p_k  = d_res_0 [k == first argmax]          (torch.max's gradient goes to one index)
+//   r_j = N_j / S, N_j = sum_k v_jk p_k, S = sum_k p_k + 1e-5
+//                              -> d v_jk = d_res_j p_k / S ;  d p_k += sum_j d_res_j (v_jk - r_j) / S
+//   p = sigmoid(o)             -> d o_k  = d p_k p_k (1 - p_k)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+yolo_reduce_bwd_kernel(const float* __restrict__ out, const float* __restrict__ d_res, float* __restrict__ d_out, long long n_pairs,
+                       int K, int A) {
+  const int lane = threadIdx.x & 31;
+  const long long pa = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (pa >= n_pairs) return;
+  const long long b = pa / A;
+  const int a = (int)(pa - b * A);
+  const float* o = out + (size_t)b * K * A * 7 + a * 7;
+  float* go = d_out + (size_t)b * K * A * 7 + a * 7;
+  float sp = 0.f, mp = -1.0f, sv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int arg = 0x7fffffff;
+  for (int k = lane; k < K; k += 32) {
+    const float* v = o + (size_t)k * A * 7;
+    const float p = 1.0f / (1.0f + expf(-v[0]));
+    sp += p;
+    if (p > mp) { mp = p; arg = k; }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sv[j] += v[1 + j] * p;
+  }
+  sp = warp_sum(sp);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {                    // (max, lowest index) reduction
+    const float om = __shfl_xor_sync(0xffffffffu, mp, d);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+    if (om > mp || (om == mp && oa < arg)) { mp = om; arg = oa; }
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) sv[j] = warp_sum(sv[j]);
+  const float S = __fadd_rn(sp, 1e-5f);
+  const float* gr = d_res + pa * 7;
+  float g[7], r[6];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) g[j] = gr[j];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) r[j] = __fdiv_rn(sv[j], S);
+  for (int k = lane; k < K; k += 32) {
+    const float* v = o + (size_t)k * A * 7;
+    float* gv = go + (size_t)k * A * 7;
+    const float p = 1.0f / (1.0f + expf(-v[0]));
+    float dp = (k == arg) ? g[0] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      gv[1 + j] = g[1 + j] * p / S;
+      dp += g[1 + j] * (v[1 + j] - r[j]) / S;
+    }
+    gv[0] = dp * p * (1.0f - p);
+  }
+}
+
 }  // namespace pnr
 
 using namespace pnr;
@@ -429,5 +484,18 @@ extern "C" int pnr_yolo_reduce(const float* out, float* result, int B, int K, in
   yolo_reduce_kernel<<<(unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       out, result, n, K, num_anchors);
   PNR_CHECK_LAUNCH("yolo_reduce_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_yolo_reduce_backward(const float* out, const float* d_result, float* d_out, int B, int K, int num_anchors,
+                                        void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(out && d_result && d_out, PNR_ERR_ARG, "pnr_yolo_reduce_backward: null pointer");
+  PNR_REQUIRE(B >= 0 && K > 0 && num_anchors > 0, PNR_ERR_ARG, "pnr_yolo_reduce_backward: bad shape");
+  if (B == 0) return PNR_OK;
+  const long long n = (long long)B * num_anchors;
+  yolo_reduce_bwd_kernel<<<(unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      out, d_result, d_out, n, K, num_anchors);
+  PNR_CHECK_LAUNCH("yolo_reduce_bwd_kernel");
   return PNR_OK;
 }

@@ -30,7 +30,7 @@ class _FieldTrainFn(torch.autograd.Function):
         pts = _lib.points_rays(a, b, sb) if mode == "rays" else _lib.points_xyz(a, b)
         P = pts.P
         cp = mlp.c_params()
-        out = torch.empty(sb, P, 4, device=dev, dtype=torch.float32)
+        out = torch.empty(sb, P, net.d_out, device=dev, dtype=torch.float32)
         tape = torch.empty(lib.pnr_field_tape_bytes(sc, pts, cp), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = lib.pnr_field_forward_train(sc, pts, cp, out.data_ptr(), tape.data_ptr(), tape.numel(),
@@ -69,6 +69,8 @@ class _FieldTrainFn(torch.autograd.Function):
 
 
 class PixelNeRFNet(torch.nn.Module):
+    TRAIN_PRECISIONS = ("fp32", "tf32", "bf16")
+
     def __init__(self, conf, stop_encoder_grad=False):
         super().__init__()
         self.encoder = make_encoder(conf["encoder"])
@@ -124,8 +126,9 @@ class PixelNeRFNet(torch.nn.Module):
         # Latents wider than the hidden width (1 792-channel YOLO maps): gather lin_z PRE-PROJECTIONS of the maps instead of
         # streaming the wide lin_z through the kernel (PNR_SCENE_PROJECTED).  None = automatic (d_latent > 512).
         self.project_wide_latent = None
-        # arithmetic of the training path's GEMMs: "fp32" (SIMT, gradients equal autograd up to summation order) or "tf32"
-        # (mma.sync tensor cores, fp32 accumulate)
+        # arithmetic of the training path's GEMMs: "fp32" (SIMT, gradients equal autograd up to summation order), "tf32"
+        # (mma.sync tensor cores, fp32 accumulate) or "bf16" (tcgen05 cta_group::2 GEMMs over a bf16 tape, fp32 accumulate in
+        # TMEM: the fast path, gradients within ~2e-2 of autograd)
         self.train_precision = "fp32"
         self.fp32_chunk_points = 50000
         self._cam_cache = None
@@ -213,6 +216,8 @@ class PixelNeRFNet(torch.nn.Module):
         sc.flags = (_lib.SCENE_MASK_NONNEG_Z | _lib.SCENE_RAW_OUTPUT) if self.yolo else 0
         if fp32_maps and self.train_precision == "tf32":
             sc.flags |= _lib.SCENE_TRAIN_TF32            # read by the training entry points only
+        elif fp32_maps and self.train_precision == "bf16":
+            sc.flags |= _lib.SCENE_TRAIN_BF16
         sc.image_w, sc.image_h, sc.lat_scale_x, sc.lat_scale_y = iw, ih, lsx, lsy
         return sc, (poses, focal, center, iw, ih, lsx, lsy)
 
@@ -349,7 +354,7 @@ class PixelNeRFNet(torch.nn.Module):
         if self._wants_grad(coarse, z):
             mlp = self._mlp(coarse)
             return _FieldTrainFn.apply(self, mlp, "rays", sb, self._train_feat(), rays.detach(), z,
-                                       *mlp.ordered_params()).reshape(Bt, K, 4)
+                                       *mlp.ordered_params()).reshape(Bt, K, self.d_out)
         if self.precision == "bf16":
             pts = _lib.points_rays(rays, z, sb)
             return self._run_field(pts, sb, Bp * K, coarse, (rays, z)).reshape(Bt, K, self.d_out)

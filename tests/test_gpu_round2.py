@@ -195,10 +195,11 @@ def test_render_plan_follows_state_changes():
     with torch.no_grad():
         assert torch.equal(b, r(fresh, rays).fine.rgb)
         assert torch.equal(b, go())                                        # and back to the first network
+    saved = net.mlp_fine.lin_out.bias.detach().clone()
     with torch.no_grad():
         net.mlp_fine.lin_out.bias.add_(0.25)                               # in-place update bumps the version
     c = go()
     assert not torch.equal(b, c)
-    net.mlp_fine.lin_out.bias.data.sub_(0.25)                              # behind autograd's back: needs invalidate()
+    net.mlp_fine.lin_out.bias.data.copy_(saved)                            # behind autograd's back: needs invalidate()
     net.mlp_fine.invalidate()
     assert torch.equal(b, go())

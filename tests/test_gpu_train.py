@@ -201,3 +201,143 @@ def test_train_step_tf32_tensor_core_arithmetic(lib):
         for name, gr in _named_grads(mlp).items():
             close(gr, g_o[lvl][name], f"tf32 {lvl} d {name}", 2e-2)
     close(lat.grad, g_o["latent"], "tf32 d latent", 2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tcgen05 training path (net.train_precision = "bf16", PNR_SCENE_TRAIN_BF16): bf16 operands, fp32 accumulation in TMEM.
+# Tolerance 2e-2 of each gradient tensor's max ("grads of all MLP params (+ latent) vs autograd, relative
+# error <= 2e-2 bf16").
+def _ws(lib, M, N, K):
+    ws = torch.empty(lib.pnr_lab_gemm_workspace_bytes(M, N, K) + 1024, dtype=torch.uint8, device="cuda")
+    return ws
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 512, 512), (1000, 512, 64), (257, 512, 1792), (128, 42, 512), (5, 1792, 512),
+                                   (40000, 512, 512)])
+def test_tcgen05_rowgemm_matches_torch(lib, M, N, K):
+    """rowgemm_kernel (csrc/train_umma.cu) alone: out = A W^T with every epilogue option, against torch on the bf16-rounded
+    inputs (fp32 accumulation: the only difference is summation order).  Shapes: one unit, ragged row tiles, K = 64 (lin_in), a
+    1792-wide contraction (wide lin_z), 42 output columns with an unaligned pitch (d zfeat), a 1792-wide output (d latent), and
+    enough units for every CTA pair to loop."""
+    from pixel_nerf_yolo_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    mask = torch.randn(M, N, generator=g).clamp_min(0)                       # a relu'd operand: ~half zeros
+    acc = A.bfloat16().float() @ W.bfloat16().float().t()
+    st = _lib.stream_ptr(torch.device("cuda", 0))
+    Ad, Wd, bd, rd, md = A.cuda(), W.cuda(), bias.cuda(), res.cuda(), mask.cuda()
+    ws = _ws(lib, M, N, K)
+    # plain: fp32 out
+    o32 = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.pnr_lab_rowgemm(Ad.data_ptr(), Wd.data_ptr(), None, None, None, o32.data_ptr(), None, M, N, K, 0, ws.data_ptr(),
+                                   ws.numel(), st), "rowgemm")
+    torch.cuda.synchronize()
+    tol = 2e-3 * max(1.0, acc.abs().max().item())
+    assert (o32.cpu() - acc).abs().max() < tol, (o32.cpu() - acc).abs().max()
+    # everything: mask, bias, residual (in place), fp32 + relu'd bf16 outputs
+    o32 = rd.clone()
+    o16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.pnr_lab_rowgemm(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), md.data_ptr(), o32.data_ptr(), o32.data_ptr(),
+                                   o16.data_ptr(), M, N, K, 1, ws.data_ptr(), ws.numel(), st), "rowgemm")
+    torch.cuda.synchronize()
+    ref = torch.where(mask.bfloat16() > 0, acc, torch.zeros_like(acc)) + bias + res
+    assert (o32.cpu() - ref).abs().max() < tol + 1e-5
+    ref16 = ref.clamp_min(0)
+    assert (o16.float().cpu() - ref16).abs().max() < tol + 2 ** -8 * max(1.0, ref16.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 256, 256), (300, 512, 512), (1000, 512, 42), (257, 512, 1792), (70000, 512, 512)])
+def test_tcgen05_wgrad_matches_torch(lib, M, N, K):
+    """wgrad_kernel alone: dW += dY^T X (both operands MN-major from row-major bf16 rows), accumulated ON TOP of existing
+    contents, against torch on the bf16-rounded inputs.  K = 42 is lin_in's weight gradient (pitch 42, one partial box)."""
+    from pixel_nerf_yolo_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    dY, X = torch.randn(M, N, generator=g), torch.randn(M, K, generator=g)
+    base = torch.randn(N, K, generator=g)
+    ref = base.double() + dY.bfloat16().double().t() @ X.bfloat16().double()
+    dW = base.cuda().clone()
+    ws = _ws(lib, M, N, K)
+    _lib.check(lib.pnr_lab_wgrad(dY.cuda().data_ptr(), X.cuda().data_ptr(), dW.data_ptr(), M, N, K, ws.data_ptr(), ws.numel(),
+                                 _lib.stream_ptr(torch.device("cuda", 0))), "wgrad")
+    torch.cuda.synchronize()
+    err = (dW.cpu().double() - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("num_objs,num_views,P,C", [(1, 3, 300, 512), (2, 2, 77, 512), (1, 1, 33, 512), (1, 3, 130, 1792)])
+def test_field_backward_bf16_matches_autograd(lib, num_objs, num_views, P, C):
+    """PixelNeRFNet.forward(xyz, viewdirs) on the tcgen05 training path: outputs and the gradients of every MLP parameter, of
+    the encoder output and of the query points vs torch autograd over the oracle.  Rows are not a multiple of the 256-row
+    tile; C = 1792 exercises the 7-block lin_z weight gradient and the 1792-wide latent gradient."""
+    import copy
+    conf = None
+    if C != 512:
+        conf = copy.deepcopy(H.MODEL_CONF)
+        conf["encoder"] = {"backbone": "custom", "pretrained": False, "num_layers": 4, "index_padding": "zeros"}
+    scene = H.make_scene_dict(num_objs=num_objs, num_views=num_views, feat=16, C=C)
+    g = torch.Generator().manual_seed(P)
+    xyz = (torch.rand(num_objs, P, 3, generator=g) - 0.5) * 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(num_objs, P, 3, generator=g), dim=-1)
+    gout = torch.randn(num_objs, P, 4, generator=g)
+    sc = H.oracle_scene(scene)
+    sc.latent = sc.latent.clone().requires_grad_(True)
+    mc = {k: v.clone().requires_grad_(True) for k, v in synth.mlp_state(1, d_latent=C).items()}
+    xo = xyz.clone().requires_grad_(True)
+    ref = O.field_forward(sc, mc, xo, dirs)
+    (ref * gout).sum().backward()
+    net = H.build_net(scene, precision="bf16", train=True, model_conf=conf)
+    lat = scene["latent"].cuda().clone().requires_grad_(True)
+    net.encoder.set_latent(lat)
+    net.train_precision = "bf16"
+    xc = xyz.cuda().requires_grad_(True)
+    out = net(xc, coarse=True, viewdirs=dirs.cuda())
+    np.testing.assert_allclose(out.detach().cpu().numpy()[..., :3], ref.detach().numpy()[..., :3], atol=1e-2, rtol=0)
+    np.testing.assert_allclose(out.detach().cpu().numpy()[..., 3], ref.detach().numpy()[..., 3], atol=1e-2, rtol=1e-2)
+    (out * gout.cuda()).sum().backward()
+    for name, gr in _named_grads(net.mlp_coarse).items():
+        close(gr, mc[name].grad, f"bf16 d {name}", 2e-2)
+    close(lat.grad, sc.latent.grad, "bf16 d latent", 2e-2)
+    close(xc.grad, xo.grad, "bf16 d xyz", 3e-2)
+
+
+def test_train_step_bf16_matches_reference_golden(lib):
+    """Full NeRFRenderer.forward + loss.backward() on the tcgen05 training path vs the reference's own autograd
+    (tests/golden/reference_grads.npz, 2 objects x 24 rays): gradients within 2e-2 of each tensor's scale."""
+    gold, scene, rays, noise, gt = golden_case()
+    net, lat = _train_net(scene)
+    net.train_precision = "bf16"
+    r = _renderer().train()
+    r.noise_override = {k: v.cuda() for k, v in noise.items()}
+    res = r(net, rays.cuda(), want_weights=True)
+    mse = torch.nn.functional.mse_loss
+    loss = mse(res.coarse.rgb, gt.cuda()) + mse(res.fine.rgb, gt.cuda())
+    loss.backward()
+    np.testing.assert_allclose(res.fine.rgb.detach().cpu().numpy(), gold["fine_rgb"], atol=1e-2, rtol=0)
+    grads = {"coarse": _named_grads(net.mlp_coarse), "fine": _named_grads(net.mlp_fine), "latent": lat.grad}
+    check_against_golden(grads, loss.item(), gold, 2e-2, "cuda bf16")
+
+
+def test_train_step_bf16_config3_full_size(lib):
+    """BASELINE config 3 at full size (4 objects x 128 rays = 245 760 view rows) on the tcgen05 path against the fp32 SIMT
+    path of this library on the same inputs (the fp32 path is pinned to autograd above): 2e-2 of each tensor's scale."""
+    num_objs, nrays = 4, 128
+    scene = H.make_scene_dict(num_objs=num_objs, num_views=3, feat=16)
+    rays = H.rays_subset(num_objs, nrays, seed=1).cuda()
+    noise = {k: v.cuda() for k, v in H.make_noise(num_objs * nrays, seed=2).items()}
+    gt = torch.rand(num_objs, nrays, 3, generator=torch.Generator().manual_seed(3)).cuda()
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        net, lat = _train_net(scene)
+        net.train_precision = prec
+        r = _renderer().train()
+        r.noise_override = noise
+        res = r(net, rays)
+        loss = ((res.coarse.rgb - gt) ** 2).mean() + ((res.fine.rgb - gt) ** 2).mean()
+        loss.backward()
+        outs[prec] = (loss.item(), _named_grads(net.mlp_coarse), _named_grads(net.mlp_fine), lat.grad)
+    assert abs(outs["bf16"][0] - outs["fp32"][0]) <= 1e-2 * abs(outs["fp32"][0])
+    for i, lvl in ((1, "coarse"), (2, "fine")):
+        for name in outs["fp32"][i]:
+            close(outs["bf16"][i][name], outs["fp32"][i][name], f"bf16 vs fp32 {lvl} d {name}", 2e-2)
+    close(outs["bf16"][3], outs["fp32"][3], "bf16 vs fp32 d latent", 2e-2)
