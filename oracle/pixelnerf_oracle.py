@@ -201,11 +201,26 @@ def bilinear_index(latent: torch.Tensor, uv: torch.Tensor, latent_scaling: torch
     return out
 
 
+def _bf16_ste(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 (round-to-nearest-even) with a straight-through gradient."""
+    return t + (t.bfloat16().float() - t).detach()
+
+
 def resnetfc_forward(p: Dict[str, torch.Tensor], zx: torch.Tensor, d_latent: int,
-                     n_blocks: int, combine_layer: int, inner_dims: Tuple[int, int]) -> torch.Tensor:
+                     n_blocks: int, combine_layer: int, inner_dims: Tuple[int, int], emulate_bf16: bool = False) -> torch.Tensor:
     """ResnetFC.forward (resnetfc.py:134-186), ReLU activations, 'average' combine.
-    ``p`` holds the module's state_dict entries (lin_in.weight, blocks.0.fc_0.weight, ...)."""
-    lin = torch.nn.functional.linear
+    ``p`` holds the module's state_dict entries (lin_in.weight, blocks.0.fc_0.weight, ...).
+    ``emulate_bf16`` (NOT reference behaviour; a test instrument for the tensor-core paths): every Linear of the trunk sees
+    its input and weight rounded to bf16 and accumulates in fp32 -- the arithmetic the tcgen05 paths define (fp32 residual
+    stream, fp32 lin_out).  Gradients flow straight through the roundings, so autograd gives the gradient of THAT forward:
+    the same ReLU masks as the CUDA path, which a comparison against the fp32 forward does not have for pre-activations
+    within the forward tolerance of zero."""
+    if emulate_bf16:
+        def lin(x, w, b, trunk=True):
+            return torch.nn.functional.linear(_bf16_ste(x), _bf16_ste(w), b) if trunk else torch.nn.functional.linear(x, w, b)
+    else:
+        def lin(x, w, b, trunk=True):
+            return torch.nn.functional.linear(x, w, b)
     z = zx[..., :d_latent]
     x = zx[..., d_latent:]
     x = lin(x, p["lin_in.weight"], p["lin_in.bias"])                        # resnetfc.py:149
@@ -219,13 +234,14 @@ def resnetfc_forward(p: Dict[str, torch.Tensor], zx: torch.Tensor, d_latent: int
         net = lin(torch.relu(x), p[f"blocks.{b}.fc_0.weight"], p[f"blocks.{b}.fc_0.bias"])
         dx = lin(torch.relu(net), p[f"blocks.{b}.fc_1.weight"], p[f"blocks.{b}.fc_1.bias"])
         x = x + dx                                                          # resnetfc.py:53-62
-    return lin(torch.relu(x), p["lin_out.weight"], p["lin_out.bias"])       # resnetfc.py:185
+    xr = _bf16_ste(torch.relu(x)) if emulate_bf16 else torch.relu(x)        # the training path's lin_out reads the bf16 operand
+    return lin(xr, p["lin_out.weight"], p["lin_out.bias"], trunk=False)     # resnetfc.py:185
 
 
 def field_forward(scene: Scene, mlp: Dict[str, torch.Tensor], xyz: torch.Tensor,
                   viewdirs: torch.Tensor, *, num_freqs: int = 6, freq_factor: float = 1.5,
                   n_blocks: int = 5, combine_layer: int = 3, padding: str = "zeros",
-                  return_raw: bool = False, yolo: bool = False) -> torch.Tensor:
+                  return_raw: bool = False, yolo: bool = False, emulate_bf16: bool = False) -> torch.Tensor:
     """PixelNeRFNet.forward (models.py:153-318) for the default_mv.conf switches
     (use_xyz, normalize_z, use_code, not use_code_viewdirs, use_viewdirs, no global encoder).
     xyz, viewdirs (SB, P, 3) -> (SB, P, 4) = [sigmoid rgb, relu sigma]."""
@@ -258,7 +274,7 @@ def field_forward(scene: Scene, mlp: Dict[str, torch.Tensor], xyz: torch.Tensor,
         nonneg = (x_cam[:, :, 2:] >= 0).reshape(-1, 1)
         lat = torch.where(nonneg | lat.isnan(), torch.zeros_like(lat), lat)
     mlp_in = torch.cat((lat, zf), dim=-1)                                   # models.py:276
-    out = resnetfc_forward(mlp, mlp_in, C, n_blocks, combine_layer, (NS, P))
+    out = resnetfc_forward(mlp, mlp_in, C, n_blocks, combine_layer, (NS, P), emulate_bf16=emulate_bf16)
     out = out.reshape(-1, P, out.shape[-1])
     if return_raw or yolo:                                                  # models.py:309-310
         return out.reshape(SB, P, -1)

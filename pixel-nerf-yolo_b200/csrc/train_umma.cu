@@ -18,6 +18,7 @@
 #include "umma.cuh"
 #include "train_umma.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace pnr {
 namespace tg {
@@ -48,8 +49,8 @@ __host__ __device__ inline uint32_t idesc_2sm(int n, int a_mn, int b_mn) {
 }
 // MN-major SWIZZLE_128B tile made of 64-feature x 64-row boxes (8 KiB each) laid one after the other along MN:
 // LBO = byte distance between 64-element MN atoms = 8 192, SBO = byte distance between 8-row K groups = 1 024
-__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo = 8192, uint32_t sbo = 1024) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -152,7 +153,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
         const bool fast = col0 + 32 <= g.n_valid;        // full chunk: staged, coalesced accesses; else the scalar tail path
         if (g.mask_src) {
-          if (fast) {
+          if (fast && (g.ld_mask & 7) == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                 // 8 rows x 64 B per instruction
               const int rr = j * 8 + (lane >> 2), cc = (lane & 3) * 8;
@@ -194,7 +195,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
         if (g.res_in) {
-          if (fast) {
+          if (fast && (g.ld_res & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {                 // 4 rows x 128 B per instruction
               const int rr = j * 4 + (lane >> 3), cc = (lane & 7) * 4;
@@ -339,10 +340,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ C
         for (long long s = s0; s < s1; ++s) {
           mbar_wait(bar(G_FULL + slot), fpar);
           const uint32_t a = sbase + SmemG::ring + slot * kStageG;
-          const uint64_t ad = smem_desc_mn(a), bd = smem_desc_mn(a + kHalf);
+          const uint64_t ad = smem_desc_mn(a, g.dbg_lbo, g.dbg_sbo), bd = smem_desc_mn(a + kHalf, g.dbg_lbo, g.dbg_sbo);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)                     // 16 rows (contraction) = 2 048 B further into both tiles
-            mma_bf16_2sm(tmem_base + buf * 256, ad + (uint64_t)(ks * 128), bd + (uint64_t)(ks * 128), idesc, (s > s0 || ks > 0) ? 1u : 0u);
+            mma_bf16_2sm(tmem_base + buf * 256, ad + (uint64_t)(ks * g.dbg_kstep), bd + (uint64_t)(ks * g.dbg_kstep), idesc, (s > s0 || ks > 0) ? 1u : 0u);
           mma_commit_2sm(bar(G_EMPTY + slot), 3);
           if (++slot == kStagesG) { slot = 0; fpar ^= 1; }
         }
@@ -503,6 +504,10 @@ int wgrad(const __nv_bfloat16* dY, long long ldy, const __nv_bfloat16* X, long l
   WgradArgs g = {};
   g.dW = dW; g.ldw = ldw; g.M = M; g.N = N; g.K = K;
   g.nNb = (N + 255) / 256; g.nKb = (K + 255) / 256;
+  g.dbg_lbo = 8192; g.dbg_sbo = 1024; g.dbg_kstep = 128;
+  if (const char* e = getenv("PNR_WGRAD_LBO")) g.dbg_lbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("PNR_WGRAD_SBO")) g.dbg_sbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("PNR_WGRAD_KSTEP")) g.dbg_kstep = (uint32_t)atoi(e);
   int max_pairs = 74;
   launch_pairs(&max_pairs);
   const long long steps = (M + 63) / 64;

@@ -31,6 +31,7 @@ struct WgradArgs {
   float* dW; int ldw;
   long long M; int N, K;
   int nNb, nKb, n_slabs;
+  uint32_t dbg_lbo, dbg_sbo, dbg_kstep;      // descriptor strides (experiments: PNR_WGRAD_LBO / SBO / KSTEP)
 };
 
 size_t packed_rowgemm_bytes(int n_out, int n_in);

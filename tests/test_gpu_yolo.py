@@ -109,7 +109,10 @@ def test_yolo_train_step_matches_reference_autograd(train_precision, rtol):
     loss = (res * T(g["gw"]).cuda()).sum()
     loss.backward()
     grads = {n: p.grad for n, p in net.mlp_coarse.named_parameters()}
-    check_yolo_grads(g, grads, lat.grad, loss.item(), res.detach().cpu().numpy(), rtol, f"cuda {train_precision}")
+    # element-wise, the sparse encoder-output gradient of the bf16-operand forward differs from the fp32 forward's by ReLU mask
+    # flips near zero (see test_field_backward_bf16_matches_autograd); its norm is held to rtol inside check_yolo_grads
+    check_yolo_grads(g, grads, lat.grad, loss.item(), res.detach().cpu().numpy(), rtol, f"cuda {train_precision}",
+                     lat_rtol=1e-1 if train_precision == "bf16" else None)
     # inference on the same (training-mode) network under no_grad takes the fused tcgen05 kernel and agrees
     with torch.no_grad():
         inf = r(rays.cuda())
