@@ -397,31 +397,43 @@ __global__ void view_mean_bwd_kernel(const float* __restrict__ dy, float* __rest
 }
 
 // bf16 path helpers -----------------------------------------------------------------------------------------------------
-// view mean that also emits the relu'd bf16 operand of the next fc_0
+// view mean that also emits the relu'd bf16 operand of the next fc_0; 4 consecutive features per thread (H % 4 == 0)
 __global__ void view_mean_bf16_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ y16, int SB, int NS,
                                       int P, int H) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)SB * P * H) return;
-  const int h = (int)(i % H);
-  const long long sp = i / H;
+  const int H4 = H >> 2;
+  if (i >= (long long)SB * P * H4) return;
+  const int h4 = (int)(i % H4);
+  const long long sp = i / H4;
   const int p = (int)(sp % P), s = (int)(sp / P);
-  float acc = 0.f;
-  for (int v = 0; v < NS; ++v) acc += x[(((long long)s * NS + v) * P + p) * H + h];
-  const float m = acc / (float)NS;
-  y[i] = m;
-  y16[i] = __float2bfloat16_rn(fmaxf(m, 0.f));
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = 0; v < NS; ++v) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + (((long long)s * NS + v) * P + p) * H) + h4);
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  const float n = (float)NS;
+  const float4 m = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+  reinterpret_cast<float4*>(y)[i] = m;
+  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(y16) + i * 2;
+  o[0] = __floats2bfloat162_rn(fmaxf(m.x, 0.f), fmaxf(m.y, 0.f));
+  o[1] = __floats2bfloat162_rn(fmaxf(m.z, 0.f), fmaxf(m.w, 0.f));
 }
 __global__ void view_mean_bwd_bf16_kernel(const float* __restrict__ dy, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int SB,
                                           int NS, int P, int H) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)SB * NS * P * H) return;
-  const int h = (int)(i % H);
-  const long long svp = i / H;
+  const int H4 = H >> 2;
+  if (i >= (long long)SB * NS * P * H4) return;
+  const int h4 = (int)(i % H4);
+  const long long svp = i / H4;
   const int p = (int)(svp % P);
   const int s = (int)(svp / P / NS);
-  const float g = dy[((long long)s * P + p) * H + h] / (float)NS;
-  dx[i] = g;
-  dx16[i] = __float2bfloat16_rn(g);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(dy + ((long long)s * P + p) * H) + h4);
+  const float n = (float)NS;
+  const float4 g = make_float4(a.x / n, a.y / n, a.z / n, a.w / n);
+  reinterpret_cast<float4*>(dx)[i] = g;
+  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dx16) + i * 2;
+  o[0] = __floats2bfloat162_rn(g.x, g.y);
+  o[1] = __floats2bfloat162_rn(g.z, g.w);
 }
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dY, float* __restrict__ db, long long M, int N, int rows_per_block) {
   const long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -468,11 +480,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 lin_out_bwd_kernel(const T* __restrict__ x, const float* __restrict__ W, const float* __restrict__ out,
                    const float* __restrict__ d_out_act, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
-                   float* __restrict__ dW, float* __restrict__ db, long long rows, int H, int d_out, int rows_per_warp, int raw) {
-  extern __shared__ float sm[];                 // [d_out][H] partial dW of this block, then [d_out] partial db
+                   float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dx_colsum, long long rows, int H, int d_out,
+                   int rows_per_warp, int raw) {
+  extern __shared__ float sm[];                 // [d_out][H] partial dW of this block, [d_out] partial db, [H] partial column sums of dx
   float* sW = sm;
   float* sb = sm + d_out * H;
-  for (int i = threadIdx.x; i < d_out * H + d_out; i += blockDim.x) sm[i] = 0.f;
+  float* sx = sb + d_out;
+  for (int i = threadIdx.x; i < d_out * H + d_out + H; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -496,9 +510,11 @@ lin_out_bwd_kernel(const T* __restrict__ x, const float* __restrict__ W, const f
       g = xv > 0.f ? g : 0.f;
       dx[row * H + k] = g;
       if (dx16) dx16[row * H + k] = __float2bfloat16_rn(g);
+      if (dx_colsum) atomicAdd(sx + k, g);
     }
   }
   __syncthreads();
+  if (dx_colsum) for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(dx_colsum + i, sx[i]);
   for (int i = threadIdx.x; i < d_out * H; i += blockDim.x) atomicAdd(dW + i, sW[i]);
   for (int i = threadIdx.x; i < d_out; i += blockDim.x) atomicAdd(db + i, sb[i]);
 }
@@ -702,12 +718,15 @@ static uint8_t* align1k(void* p) { return (uint8_t*)(((uintptr_t)p + 1023) & ~(u
 
 static int pack_all(const pnr_mlp_params* mp, int C, bool transposed, uint8_t* dst, const WPack& w, cudaStream_t st, int* launches) {
   const int H = mp->d_hidden, nb = mp->n_blocks, CL = mp->combine_layer;
-  int rc;
-#define PK(W, rows, cols, off) do { if ((rc = tg::pack_rowgemm(W, rows, cols, cols, transposed ? 1 : 0, dst + (off), st))) return rc; ++*launches; } while (0)
-  PK(mp->lin_in_w, H, mp->d_in, w.lin_in);
-  for (int b = 0; b < CL; ++b) PK(mp->linz_w[b], H, C, w.linz[b]);
-  for (int b = 0; b < nb; ++b) { PK(mp->fc0_w[b], H, H, w.fc0[b]); PK(mp->fc1_w[b], H, H, w.fc1[b]); }
-#undef PK
+  tg::PackJob jobs[tg::kMaxPackJobs];
+  int n = 0;
+  auto add = [&](const float* W, int rows, int cols, size_t off) { jobs[n++] = tg::PackJob{W, rows, cols, cols, dst + off}; };
+  add(mp->lin_in_w, H, mp->d_in, w.lin_in);
+  for (int b = 0; b < CL; ++b) add(mp->linz_w[b], H, C, w.linz[b]);
+  for (int b = 0; b < nb; ++b) { add(mp->fc0_w[b], H, H, w.fc0[b]); add(mp->fc1_w[b], H, H, w.fc1[b]); }
+  int rc = tg::pack_rowgemm_many(jobs, n, transposed ? 1 : 0, st);
+  if (rc) return rc;
+  ++*launches;
   return PNR_OK;
 }
 
@@ -751,7 +770,7 @@ static int forward_bf16(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_
     if ((rc = rg(t.RN[b], H, H, t.wpack + w.fc1[b], more ? t.lat : nullptr, C, C, more ? t.wpack + w.linz[b + 1] : nullptr, g, st, &launches))) return rc;
   }
   {
-    const long long n = pts * H;
+    const long long n = pts * H / 4;
     view_mean_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.x, t.xm, t.RXM[CL], sc->SB, sc->NS, q->P, H);      // util.py:489-499
     PNR_CHECK_LAUNCH("bwd::view_mean_bf16_kernel");
     ++launches;
@@ -801,55 +820,51 @@ static int backward_bf16(const pnr_scene* sc, const pnr_points* q, const pnr_mlp
   {
     const int rpw = 4;
     const long long warps = (pts + rpw - 1) / rpw;
-    const size_t smem = (size_t)(mp->d_out * H + mp->d_out) * sizeof(float);
+    const size_t smem = (size_t)(mp->d_out * H + mp->d_out + H) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(lin_out_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lin_out_bwd_kernel<__nv_bfloat16><<<(unsigned)((warps * 32 + 255) / 256), 256, smem, st>>>(
-        t.RXM[nb], mp->lin_out_w, out, d_out, ws.dxm, ws.dx16, gr->lin_out_w, gr->lin_out_b, pts, H, mp->d_out, rpw, raw);
+    lin_out_bwd_kernel<__nv_bfloat16><<<(unsigned)((warps * 32 + 255) / 256), 256, smem, st>>>(            // + d fc_1 bias of the last block
+        t.RXM[nb], mp->lin_out_w, out, d_out, ws.dxm, ws.dx16, gr->lin_out_w, gr->lin_out_b, gr->fc1_b[nb - 1], pts, H, mp->d_out, rpw, raw);
     PNR_CHECK_LAUNCH("bwd::lin_out_bwd_kernel");
     ++launches;
   }
 #define STEP(call) do { rc = (call); if (rc) return rc; ++launches; } while (0)
-  auto colsum16 = [&](const __nv_bfloat16* dY, float* db, long long M) -> int {
-    const int rpb = 256;
-    colsum_bf16_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>(dY, db, M, H, rpb);
-    PNR_CHECK_LAUNCH("bwd::colsum_bf16_kernel");
-    return PNR_OK;
-  };
-  // one residual block backwards (resnetfc.py:53-62); dx (fp32 master + bf16 operand copy) is updated in place
+  // Bias gradients are column sums of the gradient g_b that ENTERS block b from above (= leaves block b + 1 downwards):
+  //   d fc_1.bias[b] = colsum(g_{b+1}),  d lin_z.bias[b] = d lin_in.bias (b = 0) = colsum(g_b).
+  // Each is accumulated by the epilogue that produces the tensor (lin_out_bwd for g_nb, the dx GEMM of block b for g_b); the
+  // view-mean transpose preserves column sums (sum over views of g / NS), so g_CL's sum is taken in the post-combine space.
+  // One residual block backwards (resnetfc.py:53-62); dx (fp32 master + bf16 operand copy) is updated in place.
   auto block_bwd = [&](const __nv_bfloat16* RXb, const __nv_bfloat16* RNb, int b, float* dx, long long M) -> int {
     STEP(tg::wgrad(ws.dx16, H, RNb, H, gr->fc1_w[b], H, M, H, H, st));                          // dW1 += dx^T relu(net)
-    STEP(colsum(dx, gr->fc1_b[b], M, H, st));
     tg::RowGemmArgs g = {};                                                                      // dnet = (dx W1) * [net > 0]
-    g.M = M; g.n_valid = H; g.mask_src = RNb; g.ld_mask = H; g.out_bf16 = ws.dn16; g.ld_bf16 = H;
+    g.M = M; g.n_valid = H; g.mask_src = RNb; g.ld_mask = H; g.out_bf16 = ws.dn16; g.ld_bf16 = H; g.colsum_out = gr->fc0_b[b];
     if ((rc = rg(ws.dx16, H, H, ws.wpack + w.fc1[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
     STEP(tg::wgrad(ws.dn16, H, RXb, H, gr->fc0_w[b], H, M, H, H, st));                          // dW0 += dnet^T relu(x)
-    STEP(colsum16(ws.dn16, gr->fc0_b[b], M));
     g = {};                                                                                      // dx += (dnet W0) * [x > 0]
     g.M = M; g.n_valid = H; g.mask_src = RXb; g.ld_mask = H; g.res_in = dx; g.ld_res = H; g.out_f32 = dx; g.ld_f32 = H; g.out_bf16 = ws.dx16; g.ld_bf16 = H;
+    g.colsum_out = b >= 1 ? gr->fc1_b[b - 1] : gr->lin_in_b;
+    g.colsum_out2 = b < CL ? gr->linz_b[b] : nullptr;
     if ((rc = rg(ws.dn16, H, H, ws.wpack + w.fc0[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
     return PNR_OK;
   };
   for (int b = nb - 1; b >= CL; --b)
     if ((rc = block_bwd(t.RXM[b], t.RNM[b], b, ws.dxm, pts))) return rc;
   {
-    const long long n = rows * H;
-    view_mean_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.dxm, ws.dx, ws.dx16, sc->SB, NS, q->P, H);
+    const long long n4 = rows * H / 4;
+    view_mean_bwd_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws.dxm, ws.dx, ws.dx16, sc->SB, NS, q->P, H);
     PNR_CHECK_LAUNCH("bwd::view_mean_bwd_bf16_kernel");
     ++launches;
   }
   for (int b = CL - 1; b >= 0; --b) {
-    if ((rc = block_bwd(t.RX[b], t.RN[b], b, ws.dx, rows))) return rc;
+    if ((rc = block_bwd(t.RX[b], t.RN[b], b, ws.dx, rows))) return rc;                           // dx is now g_b, the gradient at x_b + lin_z[b](z)
     STEP(tg::wgrad(ws.dx16, H, t.lat, C, gr->linz_w[b], C, rows, H, C, st));                     // x += lin_z[b](z): resnetfc.py:176-182
-    STEP(colsum(ws.dx, gr->linz_b[b], rows, H, st));
     if (d_feat || d_xyz || d_z) {
-      tg::RowGemmArgs g = {};                                                                    // dlat (+)= dx Wz_b
+      tg::RowGemmArgs g = {};                                                                    // dlat (+)= g_b Wz_b
       g.M = rows; g.n_valid = C; g.out_f32 = ws.dlat; g.ld_f32 = C;
       if (b != CL - 1) { g.res_in = ws.dlat; g.ld_res = C; }
       if ((rc = rg(ws.dx16, H, H, ws.wpack + w.linz[b], nullptr, 0, 0, nullptr, g, st, &launches))) return rc;
     }
   }
   STEP(tg::wgrad(ws.dx16, H, t.zf, 64, gr->lin_in_w, d_in, rows, H, d_in, st));
-  STEP(colsum(ws.dx, gr->lin_in_b, rows, H, st));
 #undef STEP
   if (d_feat || d_xyz || d_z) {
     tg::RowGemmArgs g = {};                                                                      // dzf = dx W_in
@@ -956,10 +971,10 @@ extern "C" int pnr_field_backward(const pnr_scene* sc, const pnr_points* q, cons
   {
     const int rpw = 4;
     const long long warps = (pts + rpw - 1) / rpw;
-    const size_t smem = (size_t)(mp->d_out * H + mp->d_out) * sizeof(float);
+    const size_t smem = (size_t)(mp->d_out * H + mp->d_out + H) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(lin_out_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     lin_out_bwd_kernel<float><<<(unsigned)((warps * 32 + 255) / 256), 256, smem, st>>>(t.XM[nb], mp->lin_out_w, out, d_out, dA, nullptr,
-                                                                                       gr->lin_out_w, gr->lin_out_b, pts, H, mp->d_out, rpw,
+                                                                                       gr->lin_out_w, gr->lin_out_b, nullptr, pts, H, mp->d_out, rpw,
                                                                                        (sc->flags & PNR_SCENE_RAW_OUTPUT) ? 1 : 0);
     PNR_CHECK_LAUNCH("bwd::lin_out_bwd_kernel");
     ++launches;

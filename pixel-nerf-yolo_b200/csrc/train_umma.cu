@@ -30,10 +30,13 @@ constexpr int kStageG = 2 * kHalf;
 constexpr int kThreadsG = 384;                   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..11 epilogue
 constexpr int kStagePitch = 36;                  // floats per row of an epilogue staging tile (32 + 4: conflict-free 16-byte rows)
 constexpr int kStageTile = 32 * kStagePitch * 4; // 4 608 B per epilogue warp
+constexpr int kEpiTile = kStageTile + 32 * 40 * 2;   // rowgemm: + a 32 x 40 bf16 mask tile per epilogue warp
+constexpr int kThreadsR = 320;                   // rowgemm: warp 0 TMA, warp 1 TMEM alloc + MMA, warps 2..9 epilogue (quadrant = warp % 4)
 struct SmemG {
   static constexpr uint32_t ring = 0;
   static constexpr uint32_t epi = ring + kStagesG * kStageG;
-  static constexpr uint32_t bars = epi + 8 * kStageTile;
+  static constexpr uint32_t colsum = epi + 8 * kEpiTile;           // fp32 partial column sums of this CTA (<= 2 048 output columns)
+  static constexpr uint32_t bars = colsum + 2048 * 4;
   static constexpr uint32_t total = bars + 256;
 };
 enum { G_FULL = 0, G_EMPTY = G_FULL + kStagesG, G_ACC_FULL = G_EMPTY + kStagesG, G_ACC_FREE = G_ACC_FULL + 2, G_COUNT = G_ACC_FREE + 2 };
@@ -55,7 +58,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo = 
 
 // ------------------------------------------------------------------------------------------------------------------------
 template <bool kDummy>
-__global__ void __launch_bounds__(kThreadsG, 1)
+__global__ void __launch_bounds__(kThreadsR, 1)
 rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapW0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapW1, const RowGemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -73,7 +76,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int i = 0; i < 2; ++i) { mbar_init(bar(G_ACC_FULL + i), 1); mbar_init(bar(G_ACC_FREE + i), 16); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc_2sm(sbase + SmemG::bars + 8 * G_COUNT, 512);
+  if (warp == 1) tmem_alloc_2sm(sbase + SmemG::bars + 8 * G_COUNT, 512);
+  float* const csum = reinterpret_cast<float*>(smem + SmemG::colsum);
+  if (g.colsum_out) for (int i = threadIdx.x; i < g.n_pad; i += kThreadsR) csum[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -86,10 +91,35 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0) {
     if (elect_one()) {
       uint32_t slot = 0, par = 1;
+      // Every tile of this kernel is touched in 128-byte pieces (one k-block / one 32-column chunk of a row at a time), minutes
+      // apart in DRAM terms; pulling the next tile's ROWS into L2 as whole contiguous blocks keeps the HBM accesses sequential.
+      auto l2_prefetch_rows = [&](const void* base, long long ld_bytes, long long row, int n_rows) {
+        if (!base || row >= g.M) return;
+        if (row + n_rows > g.M) n_rows = (int)(g.M - row);
+        const char* p = (const char*)base + row * ld_bytes;
+        long long bytes = (long long)n_rows * ld_bytes;
+        bytes &= ~15LL;
+        for (long long off = 0; off < bytes; off += 32768) {
+          const unsigned n = (unsigned)(bytes - off < 32768 ? bytes - off : 32768);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(n) : "memory");
+        }
+      };
+      auto prefetch_tile = [&](long long u) {
+        if (u >= n_units) return;
+        const long long t = u / g.nN;
+        if (u - t * g.nN != 0) return;                       // the other feature halves of a row tile re-use what the first pulled in
+        const long long row = t * 256 + crank * 128;
+        l2_prefetch_rows(g.pf_a0, g.pf_a0_ld, row, 128);
+        l2_prefetch_rows(g.pf_a1, g.pf_a1_ld, row, 128);
+        l2_prefetch_rows(g.res_in, g.ld_res * 4, row, 128);
+        l2_prefetch_rows(g.mask_src, g.ld_mask * 2, row, 128);
+      };
+      prefetch_tile(pair_id);
       for (long long u = pair_id; u < n_units; u += n_pairs) {
         const long long t = u / g.nN;
         const int nh = (int)(u - t * g.nN);
         const int row = (int)(t * 256 + crank * 128);
+        prefetch_tile(u + n_pairs);
         for (int s = 0; s < n_stage_unit; ++s) {
           const bool second = s >= g.nK0;
           const int kb = second ? s - g.nK0 : s;
@@ -125,21 +155,70 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    const int q = warp & 3, h = (warp - 4) >> 2;
-    float* S = reinterpret_cast<float*>(smem + SmemG::epi + (warp - 4) * kStageTile);
-    __nv_bfloat16* Sb = reinterpret_cast<__nv_bfloat16*>(S);                       // bf16 view of the same tile: rows of 40 values (80 B)
-    long long i = 0;
-    for (long long u = pair_id; u < n_units; u += n_pairs, ++i) {
+  } else {
+    // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves; a unit is walked in 4 chunks of 32 columns.
+    // The global reads of a chunk (residual tile, relu-mask tile) are issued ONE CHUNK AHEAD into registers -- across unit
+    // boundaries too, before the accumulator is even complete -- so that their latency hides under the previous chunk's work.
+    const int q = warp & 3, h = warp >= 6 ? 1 : 0;
+    float* S = reinterpret_cast<float*>(smem + SmemG::epi + (warp - 2) * kEpiTile);
+    __nv_bfloat16* Sb = reinterpret_cast<__nv_bfloat16*>(S);                       // bf16 view of the fp32 tile (output staging)
+    __nv_bfloat16* Sm = reinterpret_cast<__nv_bfloat16*>(smem + SmemG::epi + (warp - 2) * kEpiTile + kStageTile);   // mask tile
+    const bool res_vec = g.res_in && (g.ld_res & 3) == 0, mask_vec = g.mask_src && (g.ld_mask & 7) == 0;
+    float4 pr[8];
+    uint4 pm[4];
+    auto chunk_pos = [&](long long u, int c, long long& row0, int& col0) {
       const long long t = u / g.nN;
       const int nh = (int)(u - t * g.nN);
+      row0 = t * 256 + crank * 128 + q * 32;
+      col0 = nh * 256 + h * 128 + c * 32;
+    };
+    auto prefetch = [&](long long u, int c) {
+      if (u >= n_units) return;
+      long long row0; int col0;
+      chunk_pos(u, c, row0, col0);
+      if (col0 + 32 > g.n_valid) return;                 // partial / empty chunk: the scalar path reads on demand
+      if (res_vec) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {                 // 4 rows x 128 B per instruction
+          const int rr = jj * 4 + (lane >> 3), cc = (lane & 7) * 4;
+          pr[jj] = (row0 + rr < g.M) ? __ldcg(reinterpret_cast<const float4*>(g.res_in + (row0 + rr) * g.ld_res + col0 + cc))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (mask_vec) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {                 // 8 rows x 64 B per instruction
+          const int rr = jj * 8 + (lane >> 2), cc = (lane & 3) * 8;
+          pm[jj] = (row0 + rr < g.M) ? __ldg(reinterpret_cast<const uint4*>(g.mask_src + (row0 + rr) * g.ld_mask + col0 + cc))
+                                     : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    };
+    long long i = 0;
+    prefetch(pair_id, 0);
+    for (long long u = pair_id; u < n_units; u += n_pairs, ++i) {
       const uint32_t buf = (uint32_t)(i & 1);
-      mbar_wait_cluster(bar(G_ACC_FULL + buf), (uint32_t)((i >> 1) & 1));
-      tc_fence_after();
-      const long long row0 = t * 256 + crank * 128 + q * 32;
+      bool acc_ready = false;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        const int col0 = nh * 256 + h * 128 + c * 32;
+        long long row0; int col0;
+        chunk_pos(u, c, row0, col0);
+        const bool fast = col0 + 32 <= g.n_valid;        // full chunk: staged, coalesced accesses; else the scalar tail path
+        // the prefetched tiles of THIS chunk go to shared memory, then the next chunk's loads are issued
+        if (fast && res_vec) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<float4*>(S + (jj * 4 + (lane >> 3)) * kStagePitch + (lane & 7) * 4) = pr[jj];
+        }
+        if (fast && mask_vec) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint4*>(Sm + (jj * 8 + (lane >> 2)) * 40 + (lane & 3) * 8) = pm[jj];
+        }
+        if (c < 3) prefetch(u, c + 1); else prefetch(u + n_pairs, 0);
+        if (!acc_ready) {
+          mbar_wait_cluster(bar(G_ACC_FULL + buf), (uint32_t)((i >> 1) & 1));
+          tc_fence_after();
+          acc_ready = true;
+        }
         uint32_t vr[32];
         tmem_ld<32>(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + h * 128 + c * 32, vr);
         if (c == 3) {                                   // last TMEM read of this unit: hand the accumulator back
@@ -147,24 +226,16 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           __syncwarp();
           if (lane == 0) { if (crank == 0) mbar_arrive(bar(G_ACC_FREE + buf)); else mbar_arrive_cluster_relaxed(lbar(G_ACC_FREE + buf)); }
         }
+        __syncwarp();                                    // the staged tiles are complete
         if (col0 >= g.n_valid) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
-        const bool fast = col0 + 32 <= g.n_valid;        // full chunk: staged, coalesced accesses; else the scalar tail path
         if (g.mask_src) {
-          if (fast && (g.ld_mask & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {                 // 8 rows x 64 B per instruction
-              const int rr = j * 8 + (lane >> 2), cc = (lane & 3) * 8;
-              uint4 m = make_uint4(0u, 0u, 0u, 0u);
-              if (row0 + rr < g.M) m = __ldg(reinterpret_cast<const uint4*>(g.mask_src + (row0 + rr) * g.ld_mask + col0 + cc));
-              *reinterpret_cast<uint4*>(Sb + rr * 40 + cc) = m;
-            }
-            __syncwarp();
+          if (fast && mask_vec) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 m = *reinterpret_cast<const uint4*>(Sb + lane * 40 + j * 8);
+              const uint4 m = *reinterpret_cast<const uint4*>(Sm + lane * 40 + j * 8);
               const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {               // bf16 > 0  <=>  sign bit clear and not zero
@@ -173,10 +244,10 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (!(hi != 0u && hi < 0x8000u)) v[j * 8 + 2 * e + 1] = 0.f;
               }
             }
-            __syncwarp();
           } else if (row0 + lane < g.M) {
-            for (int j = 0; j < 32 && col0 + j < g.n_valid; ++j)
-              if (!(__bfloat162float(g.mask_src[(row0 + lane) * g.ld_mask + col0 + j]) > 0.f)) v[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)                  // static indices: a dynamically indexed v[] would live in local memory
+              if (col0 + j < g.n_valid && !(__bfloat162float(g.mask_src[(row0 + lane) * g.ld_mask + col0 + j]) > 0.f)) v[j] = 0.f;
           }
         }
 #pragma unroll
@@ -195,24 +266,31 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
         }
         if (g.res_in) {
-          if (fast && (g.ld_res & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {                 // 4 rows x 128 B per instruction
-              const int rr = j * 4 + (lane >> 3), cc = (lane & 7) * 4;
-              float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row0 + rr < g.M) r = __ldcg(reinterpret_cast<const float4*>(g.res_in + (row0 + rr) * g.ld_res + col0 + cc));
-              *reinterpret_cast<float4*>(S + rr * kStagePitch + cc) = r;
-            }
-            __syncwarp();
+          if (fast && res_vec) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r = *reinterpret_cast<const float4*>(S + lane * kStagePitch + j * 4);
               v[j * 4] += r.x; v[j * 4 + 1] += r.y; v[j * 4 + 2] += r.z; v[j * 4 + 3] += r.w;
             }
-            __syncwarp();
           } else if (row0 + lane < g.M) {
-            for (int j = 0; j < 32 && col0 + j < g.n_valid; ++j) v[j] += g.res_in[(row0 + lane) * g.ld_res + col0 + j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.n_valid) v[j] += g.res_in[(row0 + lane) * g.ld_res + col0 + j];
           }
+        }
+        __syncwarp();                                    // every lane has read its rows: S is free for the outputs
+        if (g.colsum_out) {                              // bias gradient: sum of v over this chunk's 32 rows, per column
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = row0 + lane < g.M;
+            *reinterpret_cast<float4*>(S + lane * kStagePitch + j * 4) =
+                ok ? make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+          float cs = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) cs += S[rr * kStagePitch + lane];
+          if (col0 + lane < g.n_valid) atomicAdd(csum + col0 + lane, cs);
+          __syncwarp();
         }
         if (g.out_f32) {
           if (fast && (g.ld_f32 & 3) == 0) {
@@ -228,7 +306,8 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             __syncwarp();
           } else if (row0 + lane < g.M) {
-            for (int j = 0; j < 32 && col0 + j < g.n_valid; ++j) g.out_f32[(row0 + lane) * g.ld_f32 + col0 + j] = v[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (col0 + j < g.n_valid) g.out_f32[(row0 + lane) * g.ld_f32 + col0 + j] = v[j];
           }
         }
         if (g.out_bf16) {
@@ -254,8 +333,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             __syncwarp();
           } else if (row0 + lane < g.M) {
-            for (int j = 0; j < 32 && col0 + j < g.n_valid; ++j)
-              g.out_bf16[(row0 + lane) * g.ld_bf16 + col0 + j] = __float2bfloat16_rn(g.relu_out ? fmaxf(v[j], 0.f) : v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.n_valid) g.out_bf16[(row0 + lane) * g.ld_bf16 + col0 + j] = __float2bfloat16_rn(g.relu_out ? fmaxf(v[j], 0.f) : v[j]);
           }
         }
       }
@@ -263,8 +343,13 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (g.colsum_out)
+    for (int i = threadIdx.x; i < g.n_valid; i += kThreadsR) {
+      const float c = csum[i];
+      if (c != 0.f) { atomicAdd(g.colsum_out + i, c); if (g.colsum_out2) atomicAdd(g.colsum_out2 + i, c); }
+    }
   cluster_sync_all();
-  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -411,6 +496,25 @@ __global__ void pack_rowgemm_kernel(const float* __restrict__ W, int rows, int c
   }
 }
 
+struct PackJobs { PackJob j[kMaxPackJobs]; int first_block[kMaxPackJobs + 1]; int nK[kMaxPackJobs]; int n; int transposed; };
+__global__ void pack_rowgemm_many_kernel(const PackJobs jobs) {
+  int ji = 0;
+  while (ji + 1 < jobs.n && (int)blockIdx.x >= jobs.first_block[ji + 1]) ++ji;
+  const PackJob& J = jobs.j[ji];
+  const int local = blockIdx.x - jobs.first_block[ji];
+  const int stage = local >> 1, half = local & 1, nK = jobs.nK[ji];
+  const int nh = stage / nK, kb = stage - nh * nK;
+  uint8_t* out = (uint8_t*)J.dst + ((size_t)stage * 2 + half) * kHalf;
+  const int n_out = jobs.transposed ? J.cols : J.rows, n_in = jobs.transposed ? J.rows : J.cols;
+  for (int idx = threadIdx.x; idx < 128 * 64; idx += blockDim.x) {
+    const int r = idx >> 6, k = idx & 63;
+    const int o = nh * 256 + half * 128 + r, in = kb * 64 + k;
+    float v = 0.f;
+    if (o < n_out && in < n_in) v = jobs.transposed ? J.W[(size_t)in * J.ldw + o] : J.W[(size_t)o * J.ldw + in];
+    *reinterpret_cast<__nv_bfloat16*>(out + swz_offset(r, k)) = __float2bfloat16_rn(v);
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -439,11 +543,22 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, long long 
   return PNR_OK;
 }
 
-static int launch_pairs(int* n_pairs_out) {
+// CTA pairs that can be co-resident (persistent kernels with a static round-robin over units must not exceed it)
+template <typename K>
+static int launch_pairs(K kern, int threads, int* n_pairs_out) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  *n_pairs_out = sms / 2;
+  int pairs = sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = SmemG::total;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int mc = 0;
+  if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) == cudaSuccess && mc > 0 && mc < pairs) pairs = mc;
+  *n_pairs_out = pairs;
   return PNR_OK;
 }
 
@@ -461,14 +576,36 @@ int pack_rowgemm(const float* W, int rows, int cols, int ldw, int transposed, vo
   return PNR_OK;
 }
 
+int pack_rowgemm_many(const PackJob* jobs, int n_jobs, int transposed, cudaStream_t st) {
+  PNR_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= kMaxPackJobs, PNR_ERR_ARG, "pack_rowgemm_many: 1..%d jobs", kMaxPackJobs);
+  PackJobs pj = {};
+  pj.n = n_jobs; pj.transposed = transposed;
+  int blocks = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const int n_out = transposed ? jobs[i].cols : jobs[i].rows, n_in = transposed ? jobs[i].rows : jobs[i].cols;
+    PNR_REQUIRE(((uintptr_t)jobs[i].dst & 1023) == 0, PNR_ERR_ARG, "pack_rowgemm_many: destination must be 1024-byte aligned");
+    pj.j[i] = jobs[i];
+    pj.nK[i] = (n_in + 63) / 64;
+    pj.first_block[i] = blocks;
+    blocks += ((n_out + 255) / 256) * pj.nK[i] * 2;
+  }
+  pj.first_block[n_jobs] = blocks;
+  pack_rowgemm_many_kernel<<<blocks, 256, 0, st>>>(pj);
+  PNR_CHECK_LAUNCH("tg::pack_rowgemm_many_kernel");
+  return PNR_OK;
+}
+
 int rowgemm(const RowGemmSrc& s0, const RowGemmSrc* s1, RowGemmArgs g, cudaStream_t st) {
   if (g.M <= 0) return PNR_OK;
   PNR_REQUIRE(s0.A && s0.Wp && s0.K > 0 && s0.K % 64 == 0, PNR_ERR_ARG, "rowgemm: bad first source (K=%d)", s0.K);
   PNR_REQUIRE(g.n_valid > 0 && g.M < (1LL << 31) - 256, PNR_ERR_ARG, "rowgemm: bad shape");
   g.nN = (g.n_valid + 255) / 256;
   g.n_pad = g.nN * 256;
+  PNR_REQUIRE(!g.colsum_out || g.n_pad <= 2048, PNR_ERR_UNSUPPORTED, "rowgemm: fused column sums support up to 2048 output columns");
   g.nK0 = s0.K / 64;
   g.nK1 = s1 ? s1->K / 64 : 0;
+  g.pf_a0 = s0.A; g.pf_a0_ld = s0.lda * 2;
+  g.pf_a1 = s1 ? s1->A : nullptr; g.pf_a1_ld = s1 ? s1->lda * 2 : 0;
   CUtensorMap mA0, mW0, mA1, mW1;
   int rc;
   if ((rc = make_map(&mA0, s0.A, g.M, s0.K, s0.lda, 64, 128, true))) return rc;
@@ -482,14 +619,14 @@ int rowgemm(const RowGemmSrc& s0, const RowGemmSrc* s1, RowGemmArgs g, cudaStrea
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemG::total);
   PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int max_pairs = 74;
-  launch_pairs(&max_pairs);
+  launch_pairs(kern, kThreadsR, &max_pairs);
   const long long n_units = ((g.M + 255) / 256) * g.nN;
   const int n_pairs = (int)(n_units < max_pairs ? n_units : max_pairs);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3(n_pairs * 2); cfg.blockDim = dim3(kThreadsG); cfg.dynamicSmemBytes = SmemG::total; cfg.stream = st;
+  cfg.gridDim = dim3(n_pairs * 2); cfg.blockDim = dim3(kThreadsR); cfg.dynamicSmemBytes = SmemG::total; cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = 1;
   e = cudaLaunchKernelEx(&cfg, kern, mA0, mW0, mA1, mW1, g);
   PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "rowgemm_kernel launch: %s", cudaGetErrorString(e));
@@ -508,8 +645,10 @@ int wgrad(const __nv_bfloat16* dY, long long ldy, const __nv_bfloat16* X, long l
   if (const char* e = getenv("PNR_WGRAD_LBO")) g.dbg_lbo = (uint32_t)atoi(e);
   if (const char* e = getenv("PNR_WGRAD_SBO")) g.dbg_sbo = (uint32_t)atoi(e);
   if (const char* e = getenv("PNR_WGRAD_KSTEP")) g.dbg_kstep = (uint32_t)atoi(e);
+  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemG::total);
+  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int max_pairs = 74;
-  launch_pairs(&max_pairs);
+  launch_pairs(wgrad_kernel, kThreadsG, &max_pairs);
   const long long steps = (M + 63) / 64;
   long long slabs = (2LL * max_pairs + g.nNb * g.nKb - 1) / (g.nNb * g.nKb);      // ~2 units per CTA pair
   if (slabs > steps) slabs = steps;
@@ -523,8 +662,6 @@ int wgrad(const __nv_bfloat16* dY, long long ldy, const __nv_bfloat16* X, long l
   auto width = [](int n, long long ld) -> long long { const long long r = (n + 63) / 64 * 64; return r <= ld ? r : n; };
   if ((rc = make_map(&mY, dY, M, width(N, ldy), ldy, 64, 64, true))) return rc;
   if ((rc = make_map(&mX, X, M, width(K, ldx), ldx, 64, 64, true))) return rc;
-  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemG::total);
-  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const long long n_units = (long long)g.nNb * g.nKb * g.n_slabs;
   const int n_pairs = (int)(n_units < max_pairs ? n_units : max_pairs);
   cudaLaunchConfig_t cfg = {};

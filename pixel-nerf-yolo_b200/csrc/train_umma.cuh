@@ -20,7 +20,10 @@ struct RowGemmArgs {
   float* out_f32; long long ld_f32;
   __nv_bfloat16* out_bf16; long long ld_bf16;
   int relu_out;
+  float* colsum_out;                 // [n_valid] or null: += column sums of v over the rows (bias gradients), fused into the epilogue
+  float* colsum_out2;                // a second destination for the same sums (fc_1 bias and lin_z bias see the same gradient)
   int nN, n_pad, nK0, nK1;           // filled in by rowgemm()
+  const void* pf_a0; long long pf_a0_ld; const void* pf_a1; long long pf_a1_ld;   // operand rows for the L2 prefetch (bytes)
 };
 struct RowGemmSrc {
   const __nv_bfloat16* A; long long lda;   // [M, K] row-major bf16, lda multiple of 8
@@ -37,6 +40,10 @@ struct WgradArgs {
 size_t packed_rowgemm_bytes(int n_out, int n_in);
 // W (rows x cols, leading dimension ldw) -> packed stream; transposed = 1 packs W^T (input gradients)
 int pack_rowgemm(const float* W, int rows, int cols, int ldw, int transposed, void* dst, cudaStream_t st);
+// the same for up to kMaxPackJobs matrices in ONE launch
+constexpr int kMaxPackJobs = 24;
+struct PackJob { const float* W; int rows, cols, ldw; void* dst; };
+int pack_rowgemm_many(const PackJob* jobs, int n_jobs, int transposed, cudaStream_t st);
 int rowgemm(const RowGemmSrc& s0, const RowGemmSrc* s1, RowGemmArgs g, cudaStream_t st);
 // dW[N, K] (leading dimension ldw) += dY[M, N]^T X[M, K]; dY / X row-major bf16 with leading dimensions ldy / ldx (multiples of 8;
 // columns up to the next multiple of 64 must be readable or beyond the declared width, where TMA zero-fills)

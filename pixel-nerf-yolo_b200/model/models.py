@@ -51,7 +51,11 @@ class _FieldTrainFn(torch.autograd.Function):
         sc, _keep = net._scene_for(feat, fp32_maps=True, cams=ctx.keep)
         pts = _lib.points_rays(a, b, sb) if mode == "rays" else _lib.points_xyz(a, b)
         cp = mlp.c_params()
-        grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)      # one fill for all accumulators
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
         need_feat, need_a, need_b = ctx.needs_input_grad[4], ctx.needs_input_grad[5], ctx.needs_input_grad[6]
         d_feat = torch.zeros_like(feat) if need_feat else None
         d_xyz = torch.zeros_like(a) if (mode == "xyz" and need_a) else None
