@@ -35,8 +35,9 @@ constexpr int kThreadsR = 320;                   // rowgemm: warp 0 TMA, warp 1 
 struct SmemG {
   static constexpr uint32_t ring = 0;
   static constexpr uint32_t epi = ring + kStagesG * kStageG;
-  static constexpr uint32_t colsum = epi + 8 * kEpiTile;           // fp32 partial column sums of this CTA (<= 2 048 output columns)
-  static constexpr uint32_t bars = colsum + 2048 * 4;
+  static constexpr uint32_t colsum = epi + 8 * kEpiTile;           // fp32 partial column sums of this CTA (<= 512 output columns)
+  static constexpr uint32_t bias = colsum + 512 * 4;               // bias + bias2 of the (<= 512) output columns, staged once
+  static constexpr uint32_t bars = bias + 512 * 4;
   static constexpr uint32_t total = bars + 256;
 };
 enum { G_FULL = 0, G_EMPTY = G_FULL + kStagesG, G_ACC_FULL = G_EMPTY + kStagesG, G_ACC_FREE = G_ACC_FULL + 2, G_COUNT = G_ACC_FREE + 2 };
@@ -78,7 +79,11 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   }
   if (warp == 1) tmem_alloc_2sm(sbase + SmemG::bars + 8 * G_COUNT, 512);
   float* const csum = reinterpret_cast<float*>(smem + SmemG::colsum);
+  float* const sbias = reinterpret_cast<float*>(smem + SmemG::bias);
   if (g.colsum_out) for (int i = threadIdx.x; i < g.n_pad; i += kThreadsR) csum[i] = 0.f;
+  // the bias vectors are read from shared memory in the epilogue: 8 broadcast global loads per 32-column chunk cost ~70 us per
+  // GEMM (measured: "f32 out + bias" 137 us vs "f32 out" 70 us on 147 456 rows)
+  if (g.bias) for (int i = threadIdx.x; i < g.n_pad; i += kThreadsR) sbias[i] = i < g.n_valid ? g.bias[i] + (g.bias2 ? g.bias2[i] : 0.f) : 0.f;
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -91,42 +96,18 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0) {
     if (elect_one()) {
       uint32_t slot = 0, par = 1;
-      // Every tile of this kernel is touched in 128-byte pieces (one k-block / one 32-column chunk of a row at a time), minutes
-      // apart in DRAM terms; pulling the next tile's ROWS into L2 as whole contiguous blocks keeps the HBM accesses sequential.
-      auto l2_prefetch_rows = [&](const void* base, long long ld_bytes, long long row, int n_rows) {
-        if (!base || row >= g.M) return;
-        if (row + n_rows > g.M) n_rows = (int)(g.M - row);
-        const char* p = (const char*)base + row * ld_bytes;
-        long long bytes = (long long)n_rows * ld_bytes;
-        bytes &= ~15LL;
-        for (long long off = 0; off < bytes; off += 32768) {
-          const unsigned n = (unsigned)(bytes - off < 32768 ? bytes - off : 32768);
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(n) : "memory");
-        }
-      };
-      auto prefetch_tile = [&](long long u) {
-        if (u >= n_units) return;
-        const long long t = u / g.nN;
-        if (u - t * g.nN != 0) return;                       // the other feature halves of a row tile re-use what the first pulled in
-        const long long row = t * 256 + crank * 128;
-        l2_prefetch_rows(g.pf_a0, g.pf_a0_ld, row, 128);
-        l2_prefetch_rows(g.pf_a1, g.pf_a1_ld, row, 128);
-        l2_prefetch_rows(g.res_in, g.ld_res * 4, row, 128);
-        l2_prefetch_rows(g.mask_src, g.ld_mask * 2, row, 128);
-      };
-      prefetch_tile(pair_id);
       for (long long u = pair_id; u < n_units; u += n_pairs) {
         const long long t = u / g.nN;
         const int nh = (int)(u - t * g.nN);
         const int row = (int)(t * 256 + crank * 128);
-        prefetch_tile(u + n_pairs);
         for (int s = 0; s < n_stage_unit; ++s) {
           const bool second = s >= g.nK0;
           const int kb = second ? s - g.nK0 : s;
           const int nK = second ? g.nK1 : g.nK0;
           mbar_wait_cluster(bar(G_EMPTY + slot), par);
-          if (crank == 0) mbar_arrive_expect_tx(bar(G_FULL + slot), 2 * kStageG);
+          if (crank == 0) mbar_arrive_expect_tx(bar(G_FULL + slot), (g.diag & 2) ? kStageG : 2 * kStageG);
           const uint32_t dst = sbase + SmemG::ring + slot * kStageG;
+          if (!(g.diag & 2))      // timing diagnostic 2: no activation-tile loads (wrong results)
           tma_load_2d_2sm(dst, second ? (const void*)&mapA1 : (const void*)&mapA0, kb * 64, row, bar(G_FULL + slot));
           tma_load_2d_2sm(dst + kHalf, second ? (const void*)&mapW1 : (const void*)&mapW0, 0, ((nh * nK + kb) * 2 + (int)crank) * 128,
                           bar(G_FULL + slot));
@@ -147,6 +128,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int s = 0; s < n_stage_unit; ++s) {
           mbar_wait(bar(G_FULL + slot), fpar);
           const uint32_t a = sbase + SmemG::ring + slot * kStageG;
+          if (!(g.diag & 4))      // timing diagnostic 4: no MMAs
           mma_kblock_desc_2sm(tmem_base + buf * 256, smem_desc(a), smem_desc(a + kHalf), idesc, s > 0);
           mma_commit_2sm(bar(G_EMPTY + slot), 3);
           if (++slot == kStagesG) { slot = 0; fpar ^= 1; }
@@ -227,7 +209,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if (lane == 0) { if (crank == 0) mbar_arrive(bar(G_ACC_FREE + buf)); else mbar_arrive_cluster_relaxed(lbar(G_ACC_FREE + buf)); }
         }
         __syncwarp();                                    // the staged tiles are complete
-        if (col0 >= g.n_valid) continue;
+        if (col0 >= g.n_valid || (g.diag & 1)) continue;   // timing diagnostic 1: the epilogue only drains TMEM
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
@@ -250,19 +232,11 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               if (col0 + j < g.n_valid && !(__bfloat162float(g.mask_src[(row0 + lane) * g.ld_mask + col0 + j]) > 0.f)) v[j] = 0.f;
           }
         }
-#pragma unroll
-        for (int bi = 0; bi < 2; ++bi) {
-          const float* bias = bi == 0 ? g.bias : g.bias2;
-          if (!bias) continue;
+        if (g.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (col0 + j + 4 <= g.n_valid) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) if (col0 + j + e < g.n_valid) v[j + e] += bias[col0 + j + e];
-            }
+            const float4 b = *reinterpret_cast<const float4*>(sbias + col0 + j);      // same address in every lane: broadcast
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
         if (g.res_in) {
@@ -601,11 +575,11 @@ int rowgemm(const RowGemmSrc& s0, const RowGemmSrc* s1, RowGemmArgs g, cudaStrea
   PNR_REQUIRE(g.n_valid > 0 && g.M < (1LL << 31) - 256, PNR_ERR_ARG, "rowgemm: bad shape");
   g.nN = (g.n_valid + 255) / 256;
   g.n_pad = g.nN * 256;
-  PNR_REQUIRE(!g.colsum_out || g.n_pad <= 2048, PNR_ERR_UNSUPPORTED, "rowgemm: fused column sums support up to 2048 output columns");
+  PNR_REQUIRE((!g.colsum_out && !g.bias) || g.n_pad <= 512, PNR_ERR_UNSUPPORTED, "rowgemm: bias / fused column sums support up to 512 output columns");
+  PNR_REQUIRE(g.bias || !g.bias2, PNR_ERR_ARG, "rowgemm: bias2 without bias");
   g.nK0 = s0.K / 64;
   g.nK1 = s1 ? s1->K / 64 : 0;
-  g.pf_a0 = s0.A; g.pf_a0_ld = s0.lda * 2;
-  g.pf_a1 = s1 ? s1->A : nullptr; g.pf_a1_ld = s1 ? s1->lda * 2 : 0;
+  if (const char* e = getenv("PNR_RG_DIAG")) g.diag = atoi(e);
   CUtensorMap mA0, mW0, mA1, mW1;
   int rc;
   if ((rc = make_map(&mA0, s0.A, g.M, s0.K, s0.lda, 64, 128, true))) return rc;

@@ -23,7 +23,7 @@ struct RowGemmArgs {
   float* colsum_out;                 // [n_valid] or null: += column sums of v over the rows (bias gradients), fused into the epilogue
   float* colsum_out2;                // a second destination for the same sums (fc_1 bias and lin_z bias see the same gradient)
   int nN, n_pad, nK0, nK1;           // filled in by rowgemm()
-  const void* pf_a0; long long pf_a0_ld; const void* pf_a1; long long pf_a1_ld;   // operand rows for the L2 prefetch (bytes)
+  int diag;                          // timing diagnostics (PNR_RG_DIAG bits: 1 no epilogue work, 2 no activation loads, 4 no MMAs)
 };
 struct RowGemmSrc {
   const __nv_bfloat16* A; long long lda;   // [M, K] row-major bf16, lda multiple of 8
