@@ -43,6 +43,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return OUT
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
+    for stale in os.listdir(os.path.join(CSRC, "build")):          # objects of sources that no longer exist
+        if stale.endswith(".o") and stale[:-2] + ".cu" not in SOURCES:
+            os.remove(os.path.join(CSRC, "build", stale))
     nvcc = _nvcc()
 
     def compile_one(src):

@@ -545,9 +545,10 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     };
     auto x_epilogue = [&](int e) {                 // relu(x + cumulative bias) -> bf16 K-chunks
       for (int mt = 0; mt < kMT; ++mt) {
+        // the bias is fetched BEFORE the wait: a global load issued after it sits on the hand-off's critical path
+        const float bias = __ldg(bias_x + e * kHidden + mt * 256 + crank * 128 + fl);
         wait(B_X_FULL + mt);
         const int kc = 2 * mt + (int)crank;
-        const float bias = bias_x[e * kHidden + mt * 256 + crank * 128 + fl];
         const long long ts0 = (prof && prof_warp) ? clock64() : 0;
         convert_unit(mt * 128, kc, bias);
         if (prof && prof_warp && lane == 0) prof[14] += clock64() - ts0;
@@ -556,9 +557,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     };
     auto h_epilogue = [&](int b) {                 // relu(fc_0 out + b) -> bf16 K-chunks for fc_1
       for (int mt = 0; mt < kMT; ++mt) {
+        const float bias = __ldg(bias_h + b * kHidden + mt * 256 + crank * 128 + fl);
         wait(B_H_FULL + mt);
         const int kc = 2 * mt + (int)crank;
-        const float bias = bias_h[b * kHidden + mt * 256 + crank * 128 + fl];
         convert_unit(kHCol + mt * 128, kc, bias);
         publish(kc);
       }
@@ -571,11 +572,15 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         const int obj = tile / tiles_per_obj;
         const int p0 = (tile - obj * tiles_per_obj) * PP;
         for (int e = 0; e < sch.CL; ++e) { x_epilogue(e); h_epilogue(e); }
+        float bias_mean[kMT];
+#pragma unroll
+        for (int mt = 0; mt < kMT; ++mt) bias_mean[mt] = __ldg(bias_x + sch.CL * kHidden + mt * 256 + (int)crank * 128 + fl);
         for (int mt = 0; mt < kMT; ++mt) wait(B_X_FULL + mt);
         // view mean (combine_interleaved) + cumulative bias -> x-bar, column g*PP + p of slot hs
+#pragma unroll
         for (int mt = 0; mt < kMT; ++mt) {
           const int f = mt * 256 + (int)crank * 128 + fl;
-          const float bias = bias_x[sch.CL * kHidden + f];
+          const float bias = bias_mean[mt];
           uint32_t v[kNCol];
           tmem_ld<kNCol>(tlane + mt * 128 + hs * kNCol, v);
           if (g + 1 < G) {                          // x tile mt is in registers -> the next tile's lin_in / lin_z may overwrite it

@@ -11,7 +11,7 @@ import bench  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda", 0)
-net, renderer, rays, scene = bench.build_inputs(0, dev)
+net, renderer, rays, scene, images, state = bench.build_ours(dev)
 rays = rays[:, :: max(1, rays.shape[1] // n)][:, :n].contiguous().to(dev)
 wrapped = renderer.bind_parallel(net, None, simple_output=True).eval()
 with torch.no_grad():
