@@ -82,12 +82,15 @@ typedef struct pnr_points {
   const float* dirs;  /* mode 0: (SB, P, 3) view directions                                          */
   const float* rays;  /* mode 1: (SB*B, 8) [o, d, near, far]; point (b,k) = o + z[b,k] d             */
   const float* z;     /* mode 1: (SB*B, K) sample depths       (nerf.py:191,208-212)                 */
-  int32_t mode;       /* 0 explicit points, 1 rays x depths                                          */
+  int32_t mode;       /* 0 explicit points, 1 rays x depths, 2 rays x coarse depths computed on the fly      */
   int32_t P;          /* points per object (mode 1: B*K)                                             */
   int32_t K;          /* mode 1: samples per ray                                                     */
   int64_t total;      /* points the buffers above hold in all (xyz: total x 3, z: total); every entry point  */
                       /* requires total == scene->SB * P, so a scene encoded for more objects than the       */
                       /* caller's batch cannot run past the buffers                                           */
+  /* mode 2: z[b,k] = sample_coarse (nerf.py:104-124) evaluated where it is needed -- bit-identical to pnr_sample_coarse, */
+  /* no depth buffer and no separate launch: steps = linspace(0, 1 - 1/K, K), noise (SB*B, K) in [0,1), step = 1/K       */
+  const float* steps; const float* noise; float step; int32_t lindisp;
 } pnr_points;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -115,6 +118,15 @@ int pnr_sample_fine(const float* weights, const float* depth, const float* rays,
                     const float* u, const float* jitter, const float* gauss, float* z_out,
                     int32_t* inds_out, float* z_fine_out, float* z_depth_out, int B, int Kc, int Kf,
                     int Kfd, float depth_std, int lindisp, void* stream);
+
+/* composite of the coarse pass + the whole resampling step in ONE launch (what pnr_render_forward enqueues between the two field
+ * launches): z_coarse is recomputed from (rays, steps, noise_coarse) exactly as pnr_sample_coarse does and written to z_coarse_out,
+ * then pnr_composite and pnr_sample_fine run back to back in the same warp.  weights_coarse (B,Kc) is written (the importance
+ * sampler reads it); with n_fine == 0 only the composite part runs. */
+int pnr_composite_resample(const float* rgb_sigma, const float* rays, const float* steps, const float* noise_coarse, const float* u,
+                           const float* jitter, const float* gauss, float* z_coarse_out, float* weights_coarse, float* rgb_coarse,
+                           float* depth_coarse, float* z_fine_out, int B, int Kc, int Kf, int Kfd, float depth_std, int white_bkgd,
+                           int lindisp, void* stream);
 
 /* YoloRenderer.forward's per-ray reduction (src/render/yolo.py:96-114): raw field values out (B, K, A*7) ->
  * result (B, A, 7) = [max_k p, sum_k(v p) / (sum_k p + 1e-5)], p = sigmoid(first value of the anchor). */

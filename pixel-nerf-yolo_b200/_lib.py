@@ -27,7 +27,7 @@ SCENE_TRAIN_BF16 = 16
 EXPORTS = [
     "pnr_version", "pnr_last_error", "pnr_device_supported", "pnr_sample_coarse", "pnr_composite",
     "pnr_sample_fine", "pnr_pack_features", "pnr_gather_encode", "pnr_mlp_pack_bytes", "pnr_mlp_pack",
-    "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_gen_rays_yolo", "pnr_yolo_reduce_backward",
+    "pnr_field_workspace_bytes", "pnr_field_forward", "pnr_last_launch_count", "pnr_gen_rays_yolo", "pnr_yolo_reduce_backward", "pnr_composite_resample",
     "pnr_resnetfc_forward", "pnr_resnetfc_workspace_bytes", "pnr_positional_encoding", "pnr_index_features",
     "pnr_field_tape_bytes", "pnr_field_forward_train", "pnr_field_backward_workspace_bytes", "pnr_field_backward",
     "pnr_composite_backward", "pnr_sample_fine_depth_backward", "pnr_pyramid_pack", "pnr_gen_rays", "pnr_yolo_reduce", "pnr_image_output", "pnr_rgb_loss",
@@ -49,7 +49,8 @@ class Scene(C.Structure):
 
 class Points(C.Structure):
     _fields_ = [("xyz", C.c_void_p), ("dirs", C.c_void_p), ("rays", C.c_void_p), ("z", C.c_void_p),
-                ("mode", C.c_int32), ("P", C.c_int32), ("K", C.c_int32), ("total", C.c_int64)]
+                ("mode", C.c_int32), ("P", C.c_int32), ("K", C.c_int32), ("total", C.c_int64),
+                ("steps", C.c_void_p), ("noise", C.c_void_p), ("step", C.c_float), ("lindisp", C.c_int32)]
 
 
 def points_xyz(xyz: "torch.Tensor", dirs: Optional["torch.Tensor"]) -> Points:
@@ -174,6 +175,7 @@ def load() -> C.CDLL:
     lib.pnr_rgb_loss.argtypes = [vp, vp, vp, vp, C.c_longlong, i32, vp]
     lib.pnr_yolo_reduce.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.pnr_yolo_reduce_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.pnr_composite_resample.argtypes = [vp] * 12 + [i32, i32, i32, i32, f32, i32, i32, vp]
     lib.pnr_gen_rays.argtypes = [vp, vp, vp, C.c_longlong, i32, i32, i32, f32, f32, f32, f32, f32, f32, vp]
     lib.pnr_gen_rays_yolo.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp]
     for name in EXPORTS + LAB_EXPORTS:

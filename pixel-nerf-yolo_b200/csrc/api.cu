@@ -68,8 +68,9 @@ extern "C" int pnr_field_forward(const pnr_scene* scene, const pnr_points* pts, 
   PNR_REQUIRE(false, PNR_ERR_ARG, "pnr_field_forward: unknown precision %d", precision);
 }
 
-// ---- NeRFRenderer.forward as ONE call (src/render/nerf.py:257-309): sample_coarse -> field -> composite -> sample_fine +
-// sample_fine_depth + sort -> field -> composite, all enqueued on `stream`; every buffer is the caller's.
+// ---- NeRFRenderer.forward as ONE call (src/render/nerf.py:257-309) in FOUR launches, all enqueued on `stream`:
+//   field (coarse; sample_coarse folded into its point fetch) -> composite + sample_fine + sample_fine_depth + sort -> field (fine)
+//   -> composite.  Every buffer is the caller's.  Results are bit-identical to the stage entry points called one by one.
 namespace {
 constexpr int kMaxSplits = 4;
 struct RenderLayout { size_t z_c, out_c, w_c, z_f, out_f, field_ws, field_ws_each, total; int splits; };
@@ -154,11 +155,12 @@ static int render_slice(const pnr_render_args* a, const RenderLayout& L, long lo
   void* stream = (void*)st;
   int launches = 0, rc;
 #define RSTEP(call) do { rc = (call); if (rc) return rc; launches += pnr_last_launch_count(); } while (0)
-  RSTEP(pnr_sample_coarse(rays, a->steps, a->noise_coarse + r0 * kc, z_c, n, kc, a->lindisp, stream));
+  // launch 1: the coarse field; its sample depths are computed where they are needed (point mode 2: no sample_coarse launch)
   pnr_scene sc = *a->scene;           // SB == 1 whenever the batch is sliced; otherwise the slice is the whole batch
   pnr_points pts = {};
   const int b_obj = sc.SB == 1 ? n : a->B;
-  pts.rays = rays; pts.z = z_c; pts.mode = 1; pts.K = kc; pts.P = b_obj * kc; pts.total = (long long)n * kc;
+  pts.rays = rays; pts.mode = 2; pts.K = kc; pts.P = b_obj * kc; pts.total = (long long)n * kc;
+  pts.steps = a->steps; pts.noise = a->noise_coarse + r0 * kc; pts.step = (float)(1.0 / (double)kc); pts.lindisp = a->lindisp;
   auto mark = [&](int i) { if (a->field_events[i]) cudaEventRecord((cudaEvent_t)a->field_events[i], st); };
   mark(0);
   {
@@ -167,19 +169,20 @@ static int render_slice(const pnr_render_args* a, const RenderLayout& L, long lo
                             a->freq_factor, stream));
   }
   mark(1);
+  // launch 2: composite of the coarse pass + sample_fine + sample_fine_depth + sort (nerf.py:229-255, 290-301)
+  const int K = kc + a->n_fine;
+  float* z_f = fine ? (float*)(ws + L.z_f) + r0 * K : nullptr;
   {
     NvtxRange r("renderer_composite");
-    RSTEP(pnr_composite(out_c, z_c, rays, w_c, a->rgb_coarse + r0 * 3, a->depth_coarse + r0, n, kc, a->white_bkgd, stream));
+    RSTEP(pnr_composite_resample(out_c, rays, a->steps, a->noise_coarse + r0 * kc, fine && kf > 0 ? a->noise_u + r0 * kf : nullptr,
+                                 fine && kf > 0 ? a->noise_jitter + r0 * kf : nullptr, fine && kfd > 0 ? a->noise_gauss + r0 * kfd : nullptr,
+                                 z_c, w_c, a->rgb_coarse + r0 * 3, a->depth_coarse + r0, z_f, n, kc, fine ? kf : 0, fine ? kfd : 0,
+                                 a->depth_std, a->white_bkgd, a->lindisp, stream));
   }
   if (fine) {
-    const int K = kc + a->n_fine;
-    float* z_f = (float*)(ws + L.z_f) + r0 * K;
     float* out_f = (float*)(ws + L.out_f) + r0 * K * 4;
-    RSTEP(pnr_sample_fine(w_c, a->depth_coarse + r0, rays, z_c, a->noise_u ? a->noise_u + r0 * kf : nullptr,
-                          a->noise_jitter ? a->noise_jitter + r0 * kf : nullptr, a->noise_gauss ? a->noise_gauss + r0 * kfd : nullptr,
-                          z_f, nullptr, nullptr, nullptr, n, kc, kf, kfd, a->depth_std, a->lindisp, stream));
     pnr_scene scf = a->scene_fine ? *a->scene_fine : *a->scene;
-    pts.z = z_f; pts.K = K; pts.P = b_obj * K; pts.total = (long long)n * K;
+    pts.mode = 1; pts.z = z_f; pts.K = K; pts.P = b_obj * K; pts.total = (long long)n * K;
     const pnr_mlp_params* mf = a->mlp_fine ? a->mlp_fine : a->mlp_coarse;          // models.py:291: no fine network -> coarse
     const void* pf = a->mlp_fine ? a->packed_fine : a->packed_coarse;
     mark(2);

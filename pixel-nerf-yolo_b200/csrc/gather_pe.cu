@@ -178,6 +178,9 @@ int validate_scene_points(const pnr_scene* sc, const pnr_points* q, const char* 
   else if (q->mode == 1) {
     PNR_REQUIRE((q->rays && q->z) || q->P == 0, PNR_ERR_ARG, "%s: rays/z is null", who);
     PNR_REQUIRE(q->K > 0 && q->P % q->K == 0, PNR_ERR_ARG, "%s: P=%d is not a multiple of K=%d", who, q->P, q->K);
+  } else if (q->mode == 2) {
+    PNR_REQUIRE((q->rays && q->steps && q->noise) || q->P == 0, PNR_ERR_ARG, "%s: rays/steps/noise is null", who);
+    PNR_REQUIRE(q->K > 0 && q->P % q->K == 0, PNR_ERR_ARG, "%s: P=%d is not a multiple of K=%d", who, q->P, q->K);
   } else PNR_REQUIRE(false, PNR_ERR_ARG, "%s: unknown point mode %d", who, q->mode);
   return PNR_OK;
 }

@@ -130,6 +130,18 @@ __device__ __forceinline__ float zfeat_value_fast(const Projection& p, int j, in
   return d == 0 ? p.dx : (d == 1 ? p.dy : p.dz);
 }
 
+// near * (1 - s) + far * s (nerf.py:119,151: separately rounded), or the linear-in-disparity variant (nerf.py:121,153)
+__device__ __forceinline__ float lerp_depth(float near, float far, float s, int lindisp) {
+  if (!lindisp) return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, s)), __fmul_rn(far, s));
+  float a = __fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, s));
+  float b = __fmul_rn(__fdiv_rn(1.0f, far), s);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+// sample_coarse (nerf.py:104-124) for one (ray, sample): z_steps + rand * step, then the lerp
+__device__ __forceinline__ float coarse_depth(const float* __restrict__ ray, float step_k, float noise, float step, int lindisp) {
+  return lerp_depth(ray[6], ray[7], __fadd_rn(step_k, __fmul_rn(noise, step)), lindisp);
+}
+
 // Fetch world point + direction `idx` (flattened (object, point)) from either point source.
 __device__ __forceinline__ void fetch_point(const pnr_points& q, long long idx, float& px, float& py,
                                             float& pz, float& vx, float& vy, float& vz) {
@@ -141,7 +153,7 @@ __device__ __forceinline__ void fetch_point(const pnr_points& q, long long idx, 
   } else {
     long long ray = idx / q.K;
     const float* r = q.rays + ray * 8;
-    float zz = q.z[idx];
+    float zz = q.mode == 1 ? q.z[idx] : coarse_depth(r, q.steps[idx - ray * q.K], q.noise[idx], q.step, q.lindisp);
     vx = r[3]; vy = r[4]; vz = r[5];
     px = __fadd_rn(r[0], __fmul_rn(zz, vx));     // o + z * d, no FMA contraction (nerf.py:191)
     py = __fadd_rn(r[1], __fmul_rn(zz, vy));

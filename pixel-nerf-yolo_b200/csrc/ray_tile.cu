@@ -9,24 +9,13 @@ namespace pnr {
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxSortN = 512;   // padded (power of two) sort buffer per warp
 
-__device__ __forceinline__ float lerp_depth(float near, float far, float s, int lindisp) {
-  if (!lindisp)   // near * (1 - s) + far * s          nerf.py:119,151 (separately rounded)
-    return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, s)), __fmul_rn(far, s));
-  // 1 / (1/near * (1 - s) + 1/far * s)                nerf.py:121,153
-  float a = __fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, s));
-  float b = __fmul_rn(__fdiv_rn(1.0f, far), s);
-  return __fdiv_rn(1.0f, __fadd_rn(a, b));
-}
-
 __global__ void sample_coarse_kernel(const float* __restrict__ rays, const float* __restrict__ steps,
                                      const float* __restrict__ noise, float* __restrict__ z, int B, int Kc,
                                      float step, int lindisp) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * Kc) return;
   int b = (int)(i / Kc), k = (int)(i - (long long)b * Kc);
-  float near = rays[b * 8 + 6], far = rays[b * 8 + 7];
-  float s = __fadd_rn(steps[k], __fmul_rn(noise[i], step));   // z_steps += rand * step   nerf.py:117
-  z[i] = lerp_depth(near, far, s, lindisp);
+  z[i] = coarse_depth(rays + (size_t)b * 8, steps[k], noise[i], step, lindisp);   // z_steps += rand * step, lerp   nerf.py:117-121
 }
 
 template <typename T>
@@ -53,14 +42,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// nerf.py:184-188 + 229-255
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-composite_kernel(const float4* __restrict__ rgb_sigma, const float* __restrict__ z,
-                 const float* __restrict__ rays, float* __restrict__ weights, float* __restrict__ rgb,
-                 float* __restrict__ depth, int B, int K, int white_bkgd) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (b >= B) return;
+// nerf.py:184-188 + 229-255 for ray b, executed by one warp
+__device__ __forceinline__ void composite_ray(const float4* __restrict__ rgb_sigma, const float* __restrict__ z,
+                                              const float* __restrict__ rays, float* __restrict__ weights, float* __restrict__ rgb,
+                                              float* __restrict__ depth, int b, int K, int white_bkgd, int lane) {
   const float far = rays[b * 8 + 7];
   const float* zr = z + (size_t)b * K;
   const float4* o = rgb_sigma + (size_t)b * K;
@@ -104,6 +89,14 @@ composite_kernel(const float4* __restrict__ rgb_sigma, const float* __restrict__
     depth[b] = acc_d;
   }
 }
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_kernel(const float4* __restrict__ rgb_sigma, const float* __restrict__ z,
+                 const float* __restrict__ rays, float* __restrict__ weights, float* __restrict__ rgb,
+                 float* __restrict__ depth, int B, int K, int white_bkgd) {
+  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (b >= B) return;
+  composite_ray(rgb_sigma, z, rays, weights, rgb, depth, b, K, white_bkgd, threadIdx.x & 31);
+}
 
 // In-warp bitonic sort of n (power of two, <= kMaxSortN) floats in shared memory, ascending.
 __device__ __forceinline__ void warp_bitonic_sort(float* s, int n, int lane) {
@@ -122,21 +115,13 @@ __device__ __forceinline__ void warp_bitonic_sort(float* s, int n, int lane) {
   }
 }
 
-// nerf.py:126-167 + 300-301
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sample_fine_kernel(const float* __restrict__ weights, const float* __restrict__ depth,
-                   const float* __restrict__ rays, const float* __restrict__ z_coarse,
-                   const float* __restrict__ u, const float* __restrict__ jitter,
-                   const float* __restrict__ gauss, float* __restrict__ z_out, int32_t* __restrict__ inds_out,
-                   float* __restrict__ z_fine_out, float* __restrict__ z_depth_out, int B, int Kc, int Kf,
-                   int Kfd, float depth_std, int lindisp, int n_pad) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31;
-  const int wid = threadIdx.x >> 5;
-  const int b = blockIdx.x * kWarpsPerBlock + wid;
-  if (b >= B) return;
-  float* cdf = smem + (size_t)wid * (2 * kMaxSortN);       // Kc+1 entries
-  float* srt = cdf + kMaxSortN;                            // n_pad entries
+// nerf.py:126-167 + 300-301 for ray b, executed by one warp; cdf / srt: this warp's kMaxSortN-float scratch areas
+__device__ __forceinline__ void resample_ray(const float* __restrict__ weights, const float* __restrict__ depth,
+                                             const float* __restrict__ rays, const float* __restrict__ z_coarse,
+                                             const float* __restrict__ u, const float* __restrict__ jitter,
+                                             const float* __restrict__ gauss, float* __restrict__ z_out, int32_t* __restrict__ inds_out,
+                                             float* __restrict__ z_fine_out, float* __restrict__ z_depth_out, int b, int Kc, int Kf,
+                                             int Kfd, float depth_std, int lindisp, int n_pad, int lane, float* cdf, float* srt) {
   const float near = rays[b * 8 + 6], far = rays[b * 8 + 7];
   const int Ktot = Kc + Kf + Kfd;
 
@@ -188,6 +173,45 @@ sample_fine_kernel(const float* __restrict__ weights, const float* __restrict__ 
   __syncwarp();
   warp_bitonic_sort(srt, n_pad, lane);                     // torch.sort(cat(...))   nerf.py:300-301
   for (int i = lane; i < Ktot; i += 32) z_out[(size_t)b * Ktot + i] = srt[i];
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_fine_kernel(const float* __restrict__ weights, const float* __restrict__ depth,
+                   const float* __restrict__ rays, const float* __restrict__ z_coarse,
+                   const float* __restrict__ u, const float* __restrict__ jitter,
+                   const float* __restrict__ gauss, float* __restrict__ z_out, int32_t* __restrict__ inds_out,
+                   float* __restrict__ z_fine_out, float* __restrict__ z_depth_out, int B, int Kc, int Kf,
+                   int Kfd, float depth_std, int lindisp, int n_pad) {
+  extern __shared__ float smem[];
+  const int wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * kWarpsPerBlock + wid;
+  if (b >= B) return;
+  float* cdf = smem + (size_t)wid * (2 * kMaxSortN);       // Kc+1 entries
+  resample_ray(weights, depth, rays, z_coarse, u, jitter, gauss, z_out, inds_out, z_fine_out, z_depth_out, b, Kc, Kf, Kfd, depth_std,
+               lindisp, n_pad, threadIdx.x & 31, cdf, cdf + kMaxSortN);
+}
+
+// What pnr_render_forward runs between the two field launches, in one launch: the coarse depths are recomputed exactly as
+// sample_coarse_kernel computes them (and stored for the merge), then composite_ray and resample_ray run back to back in the warp
+// that owns the ray (its own global writes are visible to it after __syncwarp).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_resample_kernel(const float4* __restrict__ rgb_sigma, const float* __restrict__ rays, const float* __restrict__ steps,
+                          const float* __restrict__ noise, const float* __restrict__ u, const float* __restrict__ jitter,
+                          const float* __restrict__ gauss, float* __restrict__ z_coarse, float* __restrict__ weights,
+                          float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ z_fine, int B, int Kc, int Kf, int Kfd,
+                          float step, float depth_std, int white_bkgd, int lindisp, int n_pad) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * kWarpsPerBlock + wid;
+  if (b >= B) return;
+  const float* ray = rays + (size_t)b * 8;
+  for (int k = lane; k < Kc; k += 32) z_coarse[(size_t)b * Kc + k] = coarse_depth(ray, steps[k], noise[(size_t)b * Kc + k], step, lindisp);
+  __syncwarp();
+  composite_ray(rgb_sigma, z_coarse, rays, weights, rgb, depth, b, Kc, white_bkgd, lane);
+  if (Kf + Kfd == 0) return;
+  __syncwarp();
+  float* cdf = smem + (size_t)wid * (2 * kMaxSortN);
+  resample_ray(weights, depth, rays, z_coarse, u, jitter, gauss, z_fine, nullptr, nullptr, nullptr, b, Kc, Kf, Kfd, depth_std, lindisp,
+               n_pad, lane, cdf, cdf + kMaxSortN);
 }
 
 
@@ -444,6 +468,30 @@ extern "C" int pnr_sample_fine(const float* weights, const float* depth, const f
                        (cudaStream_t)stream>>>(weights, depth, rays, z_coarse, u, jitter, gauss, z_out, inds_out,
                                                z_fine_out, z_depth_out, B, Kc, Kf, Kfd, depth_std, lindisp, n_pad);
   PNR_CHECK_LAUNCH("sample_fine_kernel");
+  return PNR_OK;
+}
+
+extern "C" int pnr_composite_resample(const float* rgb_sigma, const float* rays, const float* steps, const float* noise_coarse,
+                                      const float* u, const float* jitter, const float* gauss, float* z_coarse_out,
+                                      float* weights_coarse, float* rgb_coarse, float* depth_coarse, float* z_fine_out, int B, int Kc,
+                                      int Kf, int Kfd, float depth_std, int white_bkgd, int lindisp, void* stream) {
+  reset_launch_count();
+  PNR_REQUIRE(rgb_sigma && rays && steps && noise_coarse && z_coarse_out && weights_coarse && rgb_coarse && depth_coarse, PNR_ERR_ARG,
+              "pnr_composite_resample: null pointer");
+  PNR_REQUIRE(B >= 0 && Kc > 0 && Kf >= 0 && Kfd >= 0, PNR_ERR_ARG, "pnr_composite_resample: bad shape");
+  PNR_REQUIRE(Kf + Kfd == 0 || z_fine_out, PNR_ERR_ARG, "pnr_composite_resample: z_fine_out missing");
+  PNR_REQUIRE((Kf == 0 || (u && jitter)) && (Kfd == 0 || gauss), PNR_ERR_ARG, "pnr_composite_resample: noise missing");
+  if (B == 0) return PNR_OK;
+  const int Ktot = Kc + Kf + Kfd;
+  int n_pad = 32;
+  while (n_pad < Ktot) n_pad <<= 1;
+  PNR_REQUIRE(n_pad <= kMaxSortN && Kc + 1 <= kMaxSortN, PNR_ERR_UNSUPPORTED, "pnr_composite_resample: %d samples per ray exceed the %d-entry sort buffer",
+              Ktot, kMaxSortN);
+  const size_t smem = (size_t)kWarpsPerBlock * 2 * kMaxSortN * sizeof(float);
+  composite_resample_kernel<<<(B + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      (const float4*)rgb_sigma, rays, steps, noise_coarse, u, jitter, gauss, z_coarse_out, weights_coarse, rgb_coarse, depth_coarse, z_fine_out,
+      B, Kc, Kf, Kfd, (float)(1.0 / (double)Kc), depth_std, white_bkgd, lindisp, n_pad);
+  PNR_CHECK_LAUNCH("composite_resample_kernel");
   return PNR_OK;
 }
 

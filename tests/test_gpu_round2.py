@@ -100,7 +100,7 @@ def test_config4_true_shape_subset_matches_oracle(project):
     assert net.fused_render_ready()
     with torch.no_grad():
         res = r(net, rays.cuda())
-    assert r.last_launches == 6
+    assert r.last_launches == 4
     ref = O.render(H.oracle_scene(scene), synth.mlp_state(1, d_latent=C), synth.mlp_state(2, d_latent=C), rays, _noise_obj(noise))
     for lvl in ("coarse", "fine"):
         e_rgb = (res[lvl].rgb.cpu() - ref[lvl]["rgb"]).abs().max().item()
@@ -123,7 +123,7 @@ def test_sliced_render_is_bit_identical(n_rays):
         r.noise_override = noise
         with torch.no_grad():
             outs[splits] = r(net, rays, want_weights=True)
-        expect = {1: 6, 2: 12, 3: 18, 0: 12 if n_rays >= 512 else 6}[splits]
+        expect = {1: 4, 2: 8, 3: 12, 0: 8 if n_rays >= 512 else 4}[splits]
         assert r.last_launches == expect, (splits, r.last_launches)
     torch.cuda.synchronize()
     for splits in (2, 3, 0):
