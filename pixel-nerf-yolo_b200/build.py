@@ -38,10 +38,13 @@ def _stamp() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    force = force or bool(os.environ.get("PNR_FORCE_BUILD"))
     stamp_file = os.path.join(CSRC, "build", "stamp")
     stamp = _stamp()
     if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        print(f"build: {os.path.basename(OUT)} is current (sha256 of sources + flags {stamp[:16]}); PNR_FORCE_BUILD=1 recompiles")
         return OUT
+    print(f"build: compiling {len(SOURCES)} CUDA sources for sm_100a (stamp {stamp[:16]})")
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
     for stale in os.listdir(os.path.join(CSRC, "build")):          # objects of sources that no longer exist
         if stale.endswith(".o") and stale[:-2] + ".cu" not in SOURCES:

@@ -144,3 +144,4 @@ for w in which:
     {3: config3, 4: config4, 5: config5, "yolo": yolo}[w]()
     if w == 3:
         config3("tf32")
+        config3("bf16")
