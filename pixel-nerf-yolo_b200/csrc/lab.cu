@@ -305,6 +305,114 @@ extern "C" int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid
 }
 
 
+// ---- micro-benchmark 3b: the CTA-PAIR MMA (cta_group::2, M = 256) in isolation, optionally under shared-memory traffic ----
+// Leader thread issues iters x 8 MMAs (two groups of 4 = two "stages": A from a ring of 16 KiB slots, B from 8 KiB k-blocks), a
+// multicast commit after each group when commit_every == 4.  bg: bit 0 = warps 2, 3 of each CTA stream 16 KiB bulk copies from
+// global memory into a 4-slot ring (the weight stream's shared-memory writes), bit 1 = warps 4..7 keep writing 16-byte
+// st.shared rows (the epilogue / gather stores).  out[pair] = cycles of the MMA loop.
+namespace pnr {
+__global__ void __launch_bounds__(256, 1)
+umma2_bench_kernel(int N, int iters, int commit_every, int a_slots, int bg, const uint8_t* __restrict__ src, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t crank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kA = 0, kB = 96 * 1024, kBg = 128 * 1024, kSt = 192 * 1024, kBar = 200 * 1024;
+  const uint32_t bar0 = sbase + kBar;
+  volatile int* done = reinterpret_cast<volatile int*>(smem + kBar + 256);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 12; ++i) mbar_init(bar0 + 8 * i, 1);
+    *done = 0;
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc_2sm(sbase + kBar + 128, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kBar + 128);
+  if (warp == 0) {
+    if (crank == 0) {
+      const uint32_t idesc = instr_desc_bf16_2sm(N);
+      long long t0 = 0, t1 = 0;
+      if (elect_one()) {
+        t0 = clock64();
+        int slot = 0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint64_t a = smem_desc(sbase + kA + slot * 16384), b = smem_desc(sbase + kB + g * 8192);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mma_bf16_2sm(tmem_base + ((it * 2 + g) & 1) * 256, a + 2 * u, b + 2 * u, idesc, 1);
+            if (commit_every == 4) mma_commit_2sm(bar0 + 8, 3);     // nobody waits on it
+            if (++slot >= a_slots) slot = 0;
+          }
+        }
+        mma_commit_2sm(bar0, 1);
+        mbar_wait(bar0, 0);
+        t1 = clock64();
+        out[blockIdx.x >> 1] = t1 - t0;
+      }
+      __syncwarp();
+      if (lane == 0) {                                   // stop the background warps of both CTAs
+        *done = 1;
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa_u32(sbase + kBar + 256, 1)), "r"(1) : "memory");
+      }
+    }
+  } else if ((bg & 1) && (warp == 2 || warp == 3)) {
+    if (elect_one()) {
+      const int w = warp - 2;
+      uint32_t par[2] = {0, 0};
+      const uint8_t* s0 = src + ((size_t)blockIdx.x * 2 + w) * (64 * 16384);
+      int i = 0;
+      for (; !*done; ++i) {
+        const int sl = i & 1;
+        const uint32_t b = bar0 + 8 * (2 + w * 2 + sl);
+        mbar_arrive_expect_tx(b, 16384);
+        bulk_g2s(sbase + kBg + (w * 2 + sl) * 16384, s0 + (size_t)(i & 63) * 16384, 16384, b);
+        if (i >= 1) { const int ps = (i - 1) & 1; mbar_wait(bar0 + 8 * (2 + w * 2 + ps), par[ps]); par[ps] ^= 1; }
+      }
+      if (i >= 1) { const int ps = (i - 1) & 1; mbar_wait(bar0 + 8 * (2 + w * 2 + ps), par[ps]); }   // the last copy has landed
+    }
+    __syncwarp();
+  } else if ((bg & 2) && warp >= 4) {
+    uint32_t a = sbase + kSt + ((warp - 4) * 32 + lane) * 16;
+    while (!*done) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) st_shared_v4(a + ((r * 2048) & 8191), lane, r, warp, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_2sm(tmem_base, 512);
+}
+}  // namespace pnr
+
+extern "C" int pnr_umma2_bench(int N, int iters, int commit_every, int a_slots, int bg, int pairs, const void* src, long long* out,
+                               void* stream) {
+  using namespace pnr;
+  reset_launch_count();
+  PNR_REQUIRE(out && N >= 32 && N <= 256 && N % 32 == 0 && iters > 0 && a_slots >= 1 && a_slots <= 6 && pairs >= 1, PNR_ERR_ARG,
+              "pnr_umma2_bench: bad arguments");
+  PNR_REQUIRE(!(bg & 1) || src, PNR_ERR_ARG, "pnr_umma2_bench: bg bit 0 needs a source buffer of pairs * 4 * 1 MiB");
+  const int smem = 200 * 1024 + 512;
+  cudaError_t e = cudaFuncSetAttribute(umma2_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, umma2_bench_kernel, N, iters, commit_every, a_slots, bg, (const uint8_t*)src, out);
+  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "umma2_bench launch: %s", cudaGetErrorString(e));
+  PNR_CHECK_LAUNCH("umma2_bench_kernel");
+  return PNR_OK;
+}
+
 // ---- micro-benchmark: DSMEM ping-pong of `bytes` between the two CTAs of a cluster (design aid) ------------------
 // mode 0: st.shared::cluster.v4 by `warps` warps + fence.proxy.async.shared::cluster + relaxed remote arrive
 // mode 1: one cp.async.bulk.shared::cluster.shared::cta (TMA engine) completing on the peer's mbarrier

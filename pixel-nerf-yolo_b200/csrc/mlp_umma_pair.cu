@@ -83,6 +83,17 @@ __host__ __device__ inline void fc_pair(int order, int t, int& kc, int& mt, int&
     first = pr < 2 && kk == 0; last = pr >= 6 && kk == 1;
     return;
   }
+  if (order == 3) {
+    // (c1,t0)(c0,t0)(c1,t1)(c3,t0)(c2,t0)(c0,t1)(c3,t1)(c2,t1): tile 0 is complete after FIVE pairs and tile 1 three pairs later.
+    // With hand-off latency H and P cycles per pair a layer's period is H + max(a, 10 - a) P when tile 0 completes after a
+    // pairs (chunks 2, 3 of the next layer become ready (8 - a) P after chunks 0, 1 and are first needed (a - 2) P after them):
+    // a = 5 is the minimum, one pair less than orders 1 / 2 (a = 6).
+    kc = (int)((0x23023101u >> (4 * pr)) & 0xFu);   // 1,0,1,3,2,0,3,2 (nibble pr)
+    mt = (int)((0xE4u >> pr) & 1u);                  // 0,0,1,0,0,1,1,1
+    first = (pr == 0 || pr == 2) && kk == 0;
+    last = (pr == 4 || pr == 7) && kk == 1;
+    return;
+  }
   kc = (pr < 4) ? (pr & 1) : (2 + (pr & 1));   // (c0,t0)(c1,t0)(c0,t1)(c1,t1)(c2,t0)(c3,t0)(c2,t1)(c3,t1)
   if (order == 2) kc ^= 1;                     // (c1,t0)(c0,t0)(c1,t1)(c0,t1)(c3,t0)(c2,t0)(c3,t1)(c2,t1)
   mt = (pr >> 1) & 1;
@@ -90,7 +101,7 @@ __host__ __device__ inline void fc_pair(int order, int t, int& kc, int& mt, int&
   last = (pr == 5 || pr == 7) && kk == 1;
 }
 // chunk order of lin_out (one output tile): 0,1,2,3 or, for order 2, 1,0,3,2
-__host__ __device__ inline int out_chunk(int order, int t) { return order == 2 ? ((t >> 1) ^ 1) : (t >> 1); }
+__host__ __device__ inline int out_chunk(int order, int t) { return order >= 2 ? ((t >> 1) ^ 1) : (t >> 1); }
 __host__ __device__ inline Seg walk_stage(const Sched& sc, int s) {
   Seg g;
   const int s1 = kMT * sc.KBz;
@@ -173,6 +184,7 @@ enum {
   B_RDY = B_H_FULL + kMT, B_X_FREE = B_RDY + 4,  // one per feature tile: the view-mean epilogue has read x tile mt out of TMEM
   B_LAND = B_X_FREE + kMT,                                       // non-leader CTA only: remote rows of chunk 2*i have landed (st.async bytes)
   B_OUT_FREE = B_LAND + kMT,                    // leader: the output epilogue has read lin_out's result out of the h region
+  B_C0_FREE,                                    // order 3 only: the layer's last MMAs reading chunk 0 ((c0, t1), issued AFTER tile 0 is complete) are done
   B_COUNT
 };
 static_assert(B_COUNT <= 30, "barrier parity bits live in one 32-bit word");
@@ -207,6 +219,7 @@ __device__ inline ProgEntry make_prog(const Sched& sc, int s, uint32_t sbase) {
       if (fc0) acc = first_of_tile ? 0 : 1;                      // fc_1 always accumulates into x
       if (mt == 0 && kk == 0) wait_id = B_RDY + kc + 1;          // first use of chunk kc (tile 0 precedes tile 1 for every chunk)
       if (last_of_tile) c2 = (fc0 ? B_H_FULL : B_X_FULL) + mt + 1;   // tile mt complete
+      if (sc.order == 3 && g.t == 11) c1 = B_C0_FREE + 1;          // pair 5 = (c0, t1): chunk buffer 0 may be overwritten
     } break;
     default: {
       const int kc = out_chunk(sc.order, g.t), kk = g.t % 2;
@@ -272,6 +285,15 @@ __device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* 
 // [5] wait relu(h) chunk [6] blocked in issue | [8] epilogue total [9] wait x_full [10] wait h_full [11] wait ax_free
 // [12] wait ah_free | [16] gather total [17] wait in_free    (leader CTA's MMA warp; warp 4 and warp 2 of every CTA)
 __device__ long long* g_prof_pair = nullptr;
+// optional event log of CTA pair 0 (PNR_TRACE=<file>, PROF instantiation only): role r writes (clock64 << 8 | tag) entries to
+// g_trace_pair[r * kTraceLen + n].  Roles: 0 MMA thread, 1 / 2 epilogue warp 4 of CTA 0 / 1, 3 relay, 4 gather warp 2 of CTA 0.
+// Tags: 0x10+id wait for barrier id begins, 0x40+id wait satisfied, 0x01..0x04 commit of X_FULL[0], X_FULL[1], H_FULL[0], H_FULL[1]
+// issued, 0x80 TMEM read done, 0x81 remote half stored, 0x82 local half stored, 0x83 published, 0xFF cluster start (clock alignment)
+__device__ long long* g_trace_pair = nullptr;
+__device__ int g_trace_stages = 0;      // PNR_TRACE_STAGES=1: also log every stage of the MMA thread (0x72 weights ready, 0x71 issued)
+constexpr int kTraceLen = 16384;
+#define PTRACE_L0(role_, tag_) do { if (lane == 0) PTRACE(role_, tag_); } while (0)
+#define PTRACE(role_, tag_) do { if (PROF == 2 && trace && n_tr < kTraceLen) trace[(role_) * kTraceLen + n_tr++] = (clock64() << 8) | (long long)(tag_); } while (0)
 #define PPROF_T0() const long long t0__ = prof ? clock64() : 0
 #define PPROF_ADD(slot) do { if (prof && lane == 0) prof[slot] += clock64() - t0__; } while (0)
 
@@ -290,7 +312,7 @@ __device__ long long* g_prof_pair = nullptr;
 // landing in the non-leader are counted on its B_LAND barrier, and its otherwise idle warp 1 relays that to the leader.
 // PROF = true compiles the per-role cycle counters in (PNR_PROF=1 selects that instantiation); the production instantiation
 // carries none of their branches -- the single-thread MMA issue loop is sensitive to every extra instruction.
-template <int NS, bool ASYNC, bool PROF>
+template <int NS, bool ASYNC, int PROF>   // PROF: 0 production, 1 per-role cycle counters (PNR_PROF), 2 event log of pair 0 only (PNR_TRACE)
 __global__ void __launch_bounds__(kThreads, 1)
 field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant__ CUtensorMap wmap,
                   const float* __restrict__ bias_x, const float* __restrict__ bias_h,
@@ -309,8 +331,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
   volatile uint32_t* tmem_base_slot = reinterpret_cast<volatile uint32_t*>(smem + Smem::bars + 8 * B_COUNT);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  long long* const prof = (PROF && g_prof_pair) ? reinterpret_cast<long long*>(smem + Smem::bars + 256) : nullptr;
+  long long* const prof = (PROF == 1 && g_prof_pair) ? reinterpret_cast<long long*>(smem + Smem::bars + 256) : nullptr;
   if (prof && threadIdx.x < 32) prof[threadIdx.x] = 0;
+  long long* const trace = (PROF == 2 && g_trace_pair && (blockIdx.x >> 1) == 0) ? g_trace_pair : nullptr;
+  int n_tr = 0;
+  const bool trace_stages = PROF == 2 && trace && g_trace_stages;
   auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8u * i; };
   auto lbar = [&](int i) -> uint32_t { return mapa_u32(sbase + Smem::bars + 8u * i, 0); };   // the leader's copy
   if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("pnr: dynamic smem not 1024-aligned\n"); __trap(); }
@@ -324,6 +349,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     for (int i = 0; i < 4; ++i) mbar_init(bar(B_RDY + i), kEpiWarps + ((ASYNC && (i & 1) == 0) ? 1 : 0));
     for (int i = 0; i < kMT; ++i) mbar_init(bar(B_LAND + i), kEpiWarps);
     mbar_init(bar(B_OUT_FREE), 2);
+    mbar_init(bar(B_C0_FREE), 1);
     for (int i = 0; i < kMT; ++i) mbar_init(bar(B_X_FREE + i), 2 * kEpiWarps);
     fence_barrier_init();
   }
@@ -341,6 +367,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
   cluster_sync_all();                    // both CTAs' barriers initialised and TMEM allocated before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
+  if (warp == 4) PTRACE_L0(1 + (int)crank, 0xFF);
 #ifdef PNR_DIAG_N   // timing diagnostic only (wrong results): same instruction stream, less tensor work per MMA
   const uint32_t idesc = instr_desc_bf16_2sm(PNR_DIAG_N);
 #else
@@ -358,6 +385,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         int fi = carry;
         int st = fi < G * s_pre ? fi % s_pre : fi - (G - 1) * s_pre;   // G passes over the pre stages, one over the post stages
         for (; fi < n_flat; fi += kProducers) {
+#ifdef PNR_DIAG_NORING   // timing diagnostic only (wrong results): no weight ring at all -- no loads, no full / empty handshake
+          continue;
+#endif
           mbar_wait_cluster(bar(B_W_EMPTY + slot), par);
 #ifdef PNR_DIAG_NOWEIGHTS   // timing diagnostic only (wrong results): the weight slot is declared full without loading anything
           if (crank == 0) mbar_arrive(bar(B_W_FULL + slot));
@@ -422,27 +452,36 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               if (wait_id) {
                 MPROF_T0();
                 const uint32_t id = wait_id - 1;
+                PTRACE(0, 0x10 + id);
                 mbar_wait_cluster(bar(id), (ph >> id) & 1u);
                 ph ^= (1u << id);
+                PTRACE(0, 0x40 + id);
                 if (ASYNC) fence_proxy_async();             // rows that landed in this CTA by st.async
                 tc_fence_after();                           // the other warps' tcgen05.ld / st of this TMEM precede the MMAs below
                 MPROF_ADD(id == B_IN_READY ? 2 : 4);
               }
+#ifndef PNR_DIAG_NORING
               {
                 MPROF_T0();
                 mbar_wait(full_bar, wpar);                  // completed by the TMA engine: no tcgen05 fence needed
                 MPROF_ADD(1);
+                if (trace_stages) PTRACE(0, 0x72);
               }
+#endif
               const uint64_t b_desc = bdesc_hi | (uint64_t)(cur.x & 0x3FFFu);
               const uint32_t d_col = (cur.x >> 14) & 0x1FFu;
               mma_kblock_desc_2sm(tmem_base + d_col, a_desc, b_desc, idesc, (cur.x >> 23) & 1u);
+#ifndef PNR_DIAG_NORING
               mma_commit_2sm(empty_bar, 3);
+#endif
               if (cur.y & (1u << 19)) {
                 const uint32_t c1 = cur.y & 31u, c2 = (cur.y >> 5) & 31u, c3 = (cur.y >> 14) & 31u;
                 if (c1) mma_commit_2sm(bar(c1 - 1), 3);
                 if (c2) mma_commit_2sm(bar(c2 - 1), 3);
                 if (c3) mma_commit_2sm(bar(c3 - 1), 3);
+                if (PROF == 2 && c2 > B_X_FULL && c2 <= B_X_FULL + 4) PTRACE(0, c2 - B_X_FULL);
               }
+              if (trace_stages) PTRACE(0, 0x71);
               if (++slot == kStages) { slot = 0; wpar ^= 1; full_bar = bar(B_W_FULL); empty_bar = bar(B_W_EMPTY); a_desc = wdesc0; }
               else { full_bar += 8; empty_bar += 8; a_desc += kStageStep; }
               cur = nxt;
@@ -473,9 +512,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
 #pragma unroll
           for (int mt = 0; mt < kMT; ++mt) {
             mbar_wait_cluster(bar(B_LAND + mt), par);
+            PTRACE_L0(3, 0x40 + B_LAND + mt);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(lbar(B_RDY + 2 * mt));
+            PTRACE_L0(3, 0x83);
           }
           par ^= 1;
         }
@@ -496,7 +537,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     const bool prof_warp = warp == 4;
     auto wait = [&](int id) {
       PPROF_T0();
+      if (prof_warp) PTRACE_L0(1 + (int)crank, 0x10 + id);
       mbar_wait_cluster(bar(id), (ph >> id) & 1u); ph ^= (1u << id); tc_fence_after();
+      if (prof_warp) PTRACE_L0(1 + (int)crank, 0x40 + id);
       if (prof_warp) PPROF_ADD(id < B_H_FULL ? 9 : 10);
     };
     const long long t_role0 = prof ? clock64() : 0;
@@ -527,9 +570,12 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_RDY + kc)); else mbar_arrive_cluster_relaxed(lbar(B_RDY + kc)); }
       }
       if (prof && prof_warp && lane == 0) prof[18] += clock64() - tp0;
+      if (prof_warp) PTRACE_L0(1 + (int)crank, 0x83);
     };
     // both halves of a unit: columns [hs*32, hs*32+32) of tile `peer` (remote rows) then of tile `crank` (local rows)
-    auto convert_unit = [&](uint32_t tcol, int kc, float bias) {
+    // c0_busy: (order 3) this unit rewrites chunk buffer 0 while the layer that produced it may still be reading the buffer
+    const bool order3 = sch.order == 3;
+    auto convert_unit = [&](uint32_t tcol, int kc, float bias, bool c0_busy) {
       const uint32_t loc = sbase + Smem::ring + kc * kChunkBytes;
       const uint32_t rem = mapa_u32(loc, peer);
 #ifdef PNR_DIAG_NOEPI   // timing diagnostic only (wrong results): the regular epilogues cost nothing but their barrier traffic
@@ -540,17 +586,21 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       tmem_ld_nowait<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);     // both halves in flight at once
       tmem_ld_nowait<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), u);
       tmem_ld_wait();
+      if (prof_warp) PTRACE_L0(1 + (int)crank, 0x80);
+      if (c0_busy) wait(B_C0_FREE);
       store_transposed<kNCol / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (kNCol / 2), ASYNC ? land_bar(kc) : 0u);
+      if (prof_warp) PTRACE_L0(1 + (int)crank, 0x81);
       store_transposed<kNCol / 2, false, true>(loc, u, bias, lane, qd * 32, hs * (kNCol / 2));
+      if (prof_warp) PTRACE_L0(1 + (int)crank, 0x82);
     };
-    auto x_epilogue = [&](int e) {                 // relu(x + cumulative bias) -> bf16 K-chunks
+    auto x_epilogue = [&](int e, bool after_fc) {  // relu(x + cumulative bias) -> bf16 K-chunks; after_fc: an fc_1 layer wrote this x
       for (int mt = 0; mt < kMT; ++mt) {
         // the bias is fetched BEFORE the wait: a global load issued after it sits on the hand-off's critical path
         const float bias = __ldg(bias_x + e * kHidden + mt * 256 + crank * 128 + fl);
         wait(B_X_FULL + mt);
         const int kc = 2 * mt + (int)crank;
         const long long ts0 = (prof && prof_warp) ? clock64() : 0;
-        convert_unit(mt * 128, kc, bias);
+        convert_unit(mt * 128, kc, bias, order3 && kc == 0 && after_fc);
         if (prof && prof_warp && lane == 0) prof[14] += clock64() - ts0;
         publish(kc);
       }
@@ -560,7 +610,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         const float bias = __ldg(bias_h + b * kHidden + mt * 256 + crank * 128 + fl);
         wait(B_H_FULL + mt);
         const int kc = 2 * mt + (int)crank;
-        convert_unit(kHCol + mt * 128, kc, bias);
+        convert_unit(kHCol + mt * 128, kc, bias, order3 && kc == 0);
         publish(kc);
       }
     };
@@ -571,11 +621,12 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         const bool live = tile < n_tiles;
         const int obj = tile / tiles_per_obj;
         const int p0 = (tile - obj * tiles_per_obj) * PP;
-        for (int e = 0; e < sch.CL; ++e) { x_epilogue(e); h_epilogue(e); }
+        for (int e = 0; e < sch.CL; ++e) { x_epilogue(e, e > 0); h_epilogue(e); }
         float bias_mean[kMT];
 #pragma unroll
         for (int mt = 0; mt < kMT; ++mt) bias_mean[mt] = __ldg(bias_x + sch.CL * kHidden + mt * 256 + (int)crank * 128 + fl);
         for (int mt = 0; mt < kMT; ++mt) wait(B_X_FULL + mt);
+        if (order3 && crank == 0 && sch.CL > 0) wait(B_C0_FREE);      // keep the phase in step (the last fc_1 signalled it too)
         // view mean (combine_interleaved) + cumulative bias -> x-bar, column g*PP + p of slot hs
 #pragma unroll
         for (int mt = 0; mt < kMT; ++mt) {
@@ -628,7 +679,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       }
       h_epilogue(sch.CL);
       for (int e = sch.CL + 1; e <= sch.n_blocks; ++e) {
-        x_epilogue(e);
+        x_epilogue(e, true);
         if (e < sch.n_blocks) h_epilogue(e);
       }
       // ---- output: lin_out rows are features 0..d_out-1 -> leader CTA, TMEM lanes 0..d_out-1 of h tile 0
@@ -775,7 +826,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           load_col(1, rb, wb);                       // they only fill registers
           {
             PPROF_T0();
+            if (gw == 0 && crank == 0) PTRACE_L0(4, 0x10 + B_IN_FREE);
             mbar_wait_cluster(bar(B_IN_FREE), par_free);
+            if (gw == 0 && crank == 0) PTRACE_L0(4, 0x40 + B_IN_FREE);
             if (gw == 0) PPROF_ADD(17);
           }
           par_free ^= 1;
@@ -794,6 +847,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         fence_proxy_async();                 // the gather writes this CTA's own shared memory only
         __syncwarp();
         if (lane == 0) { if (crank == 0) mbar_arrive(bar(B_IN_READY)); else mbar_arrive_cluster_relaxed(lbar(B_IN_READY)); }
+        if (gw == 0 && crank == 0) PTRACE_L0(4, 0x83);
       }
     }
     if (prof && gw == 0 && lane == 0) prof[16] += clock64() - t_role0;
@@ -801,7 +855,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (PROF && g_prof_pair && threadIdx.x < 32) g_prof_pair[(size_t)blockIdx.x * 32 + threadIdx.x] = prof[threadIdx.x];
+  if (PROF == 1 && g_prof_pair && threadIdx.x < 32) g_prof_pair[(size_t)blockIdx.x * 32 + threadIdx.x] = prof[threadIdx.x];
   cluster_sync_all();                    // no CTA exits (or frees TMEM) while the pair may still touch it
   if (warp == 1) tmem_dealloc_2sm(tmem_base, kTmemCols);
 }
@@ -819,7 +873,7 @@ static bool pair_async() {
 // and launch must agree.
 static int pair_order() {
   static int cached = -1;
-  if (cached < 0) { const char* e = getenv("PNR_ORDER"); cached = e ? atoi(e) : 2; if (cached < 0 || cached > 2) cached = 2; }
+  if (cached < 0) { const char* e = getenv("PNR_ORDER"); cached = e ? atoi(e) : 2; if (cached < 0 || cached > 3) cached = 2; }
   return cached;
 }
 static pair::Sched pair_sched(const pnr_mlp_params* p, int proj) {
@@ -891,15 +945,22 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   const bool async_x = pair_async();
   const int n_groups = ((n_tiles + 1) / 2 + G - 1) / G;  // super groups
   long long* prof_dev = nullptr;
-  if (getenv("PNR_PROF")) {
+  long long* trace_dev = nullptr;
+  if (getenv("PNR_TRACE")) {          // event log of pair 0 (takes precedence over the counters)
+    cudaMalloc(&trace_dev, (size_t)5 * pair::kTraceLen * sizeof(long long));
+    cudaMemset(trace_dev, 0, (size_t)5 * pair::kTraceLen * sizeof(long long));
+    cudaMemcpyToSymbol(pair::g_trace_pair, &trace_dev, sizeof(trace_dev));
+    const int ts = getenv("PNR_TRACE_STAGES") ? 1 : 0;
+    cudaMemcpyToSymbol(pair::g_trace_stages, &ts, sizeof(ts));
+  } else if (getenv("PNR_PROF")) {
     cudaMalloc(&prof_dev, (size_t)4096 * 32 * sizeof(long long));
     cudaMemset(prof_dev, 0, (size_t)4096 * 32 * sizeof(long long));
     cudaMemcpyToSymbol(pair::g_prof_pair, &prof_dev, sizeof(prof_dev));
   }
 #define PNR_LAUNCH_PAIR(NSV)                                                                                     \
   case NSV: {                                                                                                    \
-    auto kern = async_x ? (prof_dev ? pair::field_pair_kernel<NSV, true, true> : pair::field_pair_kernel<NSV, true, false>) \
-                        : pair::field_pair_kernel<NSV, false, false>;                                           \
+    auto kern = async_x ? (trace_dev ? pair::field_pair_kernel<NSV, true, 2> : prof_dev ? pair::field_pair_kernel<NSV, true, 1> : pair::field_pair_kernel<NSV, true, 0>) \
+                        : pair::field_pair_kernel<NSV, false, 0>;                                           \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::Smem::total); \
     PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
     cudaLaunchConfig_t cfg = {};                                                                                 \
@@ -943,6 +1004,22 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
     long long* null_ptr = nullptr;
     cudaMemcpyToSymbol(pair::g_prof_pair, &null_ptr, sizeof(null_ptr));
     cudaFree(prof_dev);
+
+  }
+  if (trace_dev) {
+    cudaStreamSynchronize(st);
+    long long* null_ptr = nullptr;
+    std::vector<long long> tr((size_t)5 * pair::kTraceLen);
+    cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("PNR_TRACE"), "a")) {
+      fprintf(f, "# launch tiles=%d\n", n_tiles);
+      for (int r = 0; r < 5; ++r)
+        for (int i = 0; i < pair::kTraceLen && tr[(size_t)r * pair::kTraceLen + i]; ++i)
+          fprintf(f, "%d %lld %lld\n", r, tr[(size_t)r * pair::kTraceLen + i] >> 8, tr[(size_t)r * pair::kTraceLen + i] & 0xFF);
+      fclose(f);
+    }
+    cudaMemcpyToSymbol(pair::g_trace_pair, &null_ptr, sizeof(null_ptr));
+    cudaFree(trace_dev);
   }
   return PNR_OK;
 }

@@ -19,6 +19,9 @@ int pnr_ingest_bench_tma(const void* src, int src_stages, int n_stages, int dept
                          int box_rows, int swizzle, void* stream);
 /* cycles for `iters` x 8 tcgen05.mma (kind::f16, bf16, K=16) of shape M x N issued back to back from shared-memory operands. */
 int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid, long long* out, int commit_every, void* stream);
+/* the CTA-pair MMA (cta_group::2, M = 256, N) in isolation: out[pairs] = cycles for iters x 8 MMAs; bg bit 0 = concurrent 16 KiB
+ * bulk copies from src (pairs * 4 MiB) into shared memory, bit 1 = concurrent st.shared traffic. */
+int pnr_umma2_bench(int N, int iters, int commit_every, int a_slots, int bg, int pairs, const void* src, long long* out, void* stream);
 /* distributed-shared-memory ping-pong of `bytes` between the two CTAs of a cluster.  mode 0: st.shared::cluster.v4 by `warps`
  * warps + proxy fence + remote arrive; mode 1: one cp.async.bulk smem->peer smem.  out[2] = cycles for `iters` transfers. */
 int pnr_dsmem_bench(int mode, int bytes, int iters, int warps, long long* out, void* stream);

@@ -19,4 +19,8 @@ build_one nogather -DPNR_DIAG_NOGATHER &
 build_one noweights_noepi -DPNR_DIAG_NOWEIGHTS -DPNR_DIAG_NOEPI &
 build_one none3 -DPNR_DIAG_NOWEIGHTS -DPNR_DIAG_NOEPI -DPNR_DIAG_NOGATHER &
 wait
+build_one noring -DPNR_DIAG_NORING &
+build_one noring_noepi -DPNR_DIAG_NORING -DPNR_DIAG_NOEPI &
+build_one noring_none3 -DPNR_DIAG_NORING -DPNR_DIAG_NOEPI -DPNR_DIAG_NOGATHER &
+wait
 ls -la $D/*.so

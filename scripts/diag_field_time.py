@@ -19,7 +19,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 import bench  # noqa: E402
 
 dev = torch.device("cuda", 0)
-net, renderer, rays, scene = bench.build_inputs(0, dev)
+net, renderer, rays, scene, images, state = bench.build_ours(dev)
 rays = rays.reshape(-1, 8).contiguous().to(dev)
 B = rays.shape[0]
 g = torch.Generator(device=dev).manual_seed(0)
