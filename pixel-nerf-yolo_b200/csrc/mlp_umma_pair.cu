@@ -36,6 +36,20 @@ using namespace umma;
 
 namespace pair {
 
+// Timing diagnostics (WRONG RESULTS, scripts/build_diag_variants.sh): PNR_DIAG_MMAONLY = the MMA thread's instruction stream alone;
+// its parts can be switched off one by one: OFF_RING (no weight stream, no W_FULL wait), OFF_WAITS (the MMA thread waits for no
+// epilogue / gather barrier), OFF_EPI (no epilogue / relay warps), OFF_GATHER (no gather warps).
+#ifdef PNR_DIAG_MMAONLY
+#define PNR_DIAG_OFF_RING
+#define PNR_DIAG_OFF_WAITS
+#define PNR_DIAG_OFF_EPI
+#define PNR_DIAG_OFF_GATHER
+#endif
+#ifdef PNR_DIAG_NORING
+#define PNR_DIAG_OFF_RING
+#define PNR_DIAG_OFF_EMPTY_COMMIT
+#endif
+
 constexpr int kNCol = 64;                    // columns per CTA tile
 constexpr int kMT = 2;                       // 256-feature tiles per 512-wide layer
 constexpr int kKBlocksH = kHidden / kBlockK; // 8
@@ -261,6 +275,10 @@ __device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* 
     // pair column j with column j+8: after the transpose lane i owns rows c0+i and c0+8+i, whose (row & 7) differ
     // across the 8 lanes of a group -> the swizzled 16-byte stores of a quarter warp hit 8 different bank groups
     uint32_t p[8];
+#ifdef PNR_DIAG_EPI_NOALU   // timing diagnostic only (wrong results): the epilogue's stores without its arithmetic / TMEM reads
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = (uint32_t)(lane + j + c0);
+#else
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float x = __uint_as_float(vals[c0 + j]), y = __uint_as_float(vals[c0 + 8 + j]);
@@ -268,12 +286,16 @@ __device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* 
       p[j] = pack_relu_bf16x2(x, y);
     }
     transpose8x8(p, lane);                                      // p[f] = (feature 8g+f at column c0+i, at column c0+8+i)
+#endif
     const uint32_t e0 = __byte_perm(p[0], p[1], 0x5410), e1 = __byte_perm(p[2], p[3], 0x5410);
     const uint32_t e2 = __byte_perm(p[4], p[5], 0x5410), e3 = __byte_perm(p[6], p[7], 0x5410);
     const uint32_t o0 = __byte_perm(p[0], p[1], 0x7632), o1 = __byte_perm(p[2], p[3], 0x7632);
     const uint32_t o2 = __byte_perm(p[4], p[5], 0x7632), o3 = __byte_perm(p[6], p[7], 0x7632);
     const uint32_t addr_e = base + kb_off + swz_offset(row0 + c0 + i, k & 63);
     const uint32_t addr_o = base + kb_off + swz_offset(row0 + c0 + 8 + i, k & 63);
+#ifdef PNR_DIAG_EPI_NOSTORE   // timing diagnostic only (wrong results): all of the epilogue's arithmetic, none of its stores
+    if ((e0 ^ e1 ^ e2 ^ e3 ^ o0 ^ o1 ^ o2 ^ o3) != 0x9E3779B9u) continue;
+#endif
     if (REMOTE) {
       if (async_bar) { st_async_v4(addr_e, e0, e1, e2, e3, async_bar); st_async_v4(addr_o, o0, o1, o2, o3, async_bar); }
       else { st_cluster_v4(addr_e, e0, e1, e2, e3); st_cluster_v4(addr_o, o0, o1, o2, o3); }
@@ -286,7 +308,8 @@ __device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* 
 // [12] wait ah_free | [16] gather total [17] wait in_free    (leader CTA's MMA warp; warp 4 and warp 2 of every CTA)
 __device__ long long* g_prof_pair = nullptr;
 // optional event log of CTA pair 0 (PNR_TRACE=<file>, PROF instantiation only): role r writes (clock64 << 8 | tag) entries to
-// g_trace_pair[r * kTraceLen + n].  Roles: 0 MMA thread, 1 / 2 epilogue warp 4 of CTA 0 / 1, 3 relay, 4 gather warp 2 of CTA 0.
+// g_trace_pair[r * kTraceLen + n].  Roles: 0 MMA thread, 1 / 2 epilogue warp 4 of CTA 0 / 1, 3 relay, 4 gather warp 2 of CTA 0, 5..7 weight producers of CTA 0
+// (0x84 = TMA issued).
 // Tags: 0x10+id wait for barrier id begins, 0x40+id wait satisfied, 0x01..0x04 commit of X_FULL[0], X_FULL[1], H_FULL[0], H_FULL[1]
 // issued, 0x80 TMEM read done, 0x81 remote half stored, 0x82 local half stored, 0x83 published, 0xFF cluster start (clock alignment)
 __device__ long long* g_trace_pair = nullptr;
@@ -385,16 +408,23 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         int fi = carry;
         int st = fi < G * s_pre ? fi % s_pre : fi - (G - 1) * s_pre;   // G passes over the pre stages, one over the post stages
         for (; fi < n_flat; fi += kProducers) {
-#ifdef PNR_DIAG_NORING   // timing diagnostic only (wrong results): no weight ring at all -- no loads, no full / empty handshake
+#ifdef PNR_DIAG_OFF_RING   // timing diagnostic only (wrong results): no weight ring at all
           continue;
 #endif
+          if (crank == 0) PTRACE(5 + pid, 0x10 + B_W_EMPTY + slot);
+#if PNR_IDLE_WAIT
+          mbar_wait_idle(bar(B_W_EMPTY + slot), par);
+#else
           mbar_wait_cluster(bar(B_W_EMPTY + slot), par);
+#endif
+          if (crank == 0) PTRACE(5 + pid, 0x40 + B_W_EMPTY + slot);
 #ifdef PNR_DIAG_NOWEIGHTS   // timing diagnostic only (wrong results): the weight slot is declared full without loading anything
           if (crank == 0) mbar_arrive(bar(B_W_FULL + slot));
 #else
           if (crank == 0) mbar_arrive_expect_tx(bar(B_W_FULL + slot), 2 * kStageBytes);
           tma_load_2d_2sm(sbase + Smem::w + slot * kStageBytes, &wmap, 0, (st * 2 + (int)crank) * kStageRows, bar(B_W_FULL + slot));
 #endif
+          if (crank == 0) PTRACE(5 + pid, 0x84);
           slot += kProducers;
           if (slot >= kStages) { slot -= kStages; par ^= 1; }
           // next stage id without a division: inside the pre passes the id wraps at s_pre, after them it just continues
@@ -431,7 +461,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               // the view-mean epilogue of the previous tile must have read x tile 0 out of TMEM before lin_in (stage 0) overwrites
               // it; tile 1 is first written by stage 1 (see below)
               MPROF_T0();
+#ifndef PNR_DIAG_OFF_WAITS
               mbar_wait_cluster(bar(B_X_FREE), (ph >> B_X_FREE) & 1u);
+#endif
               ph ^= (1u << B_X_FREE);
               tc_fence_after();
               MPROF_ADD(5);
@@ -441,7 +473,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               // The previous super group's output epilogue (two warps of this CTA) reads lin_out's result from h tile 0; the first
               // fc_0 of this super group only waits for a chunk signalled by the OTHER CTA's warps (odd-chunk-first order).  In
               // practice that is thousands of cycles later; this wait (a few hundred cycles after lin_out at most) makes it explicit.
+#ifndef PNR_DIAG_OFF_WAITS
               mbar_wait(bar(B_OUT_FREE), (ph >> B_OUT_FREE) & 1u);
+#endif
               ph ^= (1u << B_OUT_FREE);
             }
             uint2 cur = prog[st_beg];
@@ -453,14 +487,16 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
                 MPROF_T0();
                 const uint32_t id = wait_id - 1;
                 PTRACE(0, 0x10 + id);
+#ifndef PNR_DIAG_OFF_WAITS   // timing diagnostic only (wrong results): the MMA thread's instruction stream alone, nothing to wait for
                 mbar_wait_cluster(bar(id), (ph >> id) & 1u);
+#endif
                 ph ^= (1u << id);
                 PTRACE(0, 0x40 + id);
                 if (ASYNC) fence_proxy_async();             // rows that landed in this CTA by st.async
                 tc_fence_after();                           // the other warps' tcgen05.ld / st of this TMEM precede the MMAs below
                 MPROF_ADD(id == B_IN_READY ? 2 : 4);
               }
-#ifndef PNR_DIAG_NORING
+#ifndef PNR_DIAG_OFF_RING
               {
                 MPROF_T0();
                 mbar_wait(full_bar, wpar);                  // completed by the TMA engine: no tcgen05 fence needed
@@ -471,8 +507,8 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
               const uint64_t b_desc = bdesc_hi | (uint64_t)(cur.x & 0x3FFFu);
               const uint32_t d_col = (cur.x >> 14) & 0x1FFu;
               mma_kblock_desc_2sm(tmem_base + d_col, a_desc, b_desc, idesc, (cur.x >> 23) & 1u);
-#ifndef PNR_DIAG_NORING
-              mma_commit_2sm(empty_bar, 3);
+#ifndef PNR_DIAG_OFF_EMPTY_COMMIT
+              mma_commit_2sm(empty_bar, 3);       // (kept under PNR_DIAG_MMAONLY: nobody waits on it)
 #endif
               if (cur.y & (1u << 19)) {
                 const uint32_t c1 = cur.y & 31u, c2 = (cur.y >> 5) & 31u, c3 = (cur.y >> 14) & 31u;
@@ -490,7 +526,9 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
             if (after_mean) {                               // lin_in's second stage is the first write into x tile 1
               issue_stage(st++);
               MPROF_T0();
+#ifndef PNR_DIAG_OFF_WAITS
               mbar_wait_cluster(bar(B_X_FREE + 1), (ph >> (B_X_FREE + 1)) & 1u);
+#endif
               ph ^= (1u << (B_X_FREE + 1));
               tc_fence_after();
               MPROF_ADD(5);
@@ -503,7 +541,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       }
       __syncwarp();
       if (prof && lane == 0) prof[0] += clock64() - t_role0;
+#ifdef PNR_DIAG_OFF_EPI
+    } else if (false) {
+#else
     } else if (ASYNC) {
+#endif
       // ===================== relay (non-leader CTA): remote rows of the even chunks have landed here -> tell the leader
       const int n_pub = G * 2 * sch.CL + 2 * (sch.n_blocks - sch.CL) + 1;     // publishes of each chunk per super group
       uint32_t par = 0;
@@ -522,7 +564,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         }
       }
     }
+#ifdef PNR_DIAG_OFF_EPI
+  } else if (false) {
+#else
   } else if (warp >= 4 && warp < 12) {
+#endif
     // ===================== epilogue warps ===================================================================
     // 8 warps = 4 TMEM lane quadrants (qd) x 2.  Unit = this CTA's 128 features of feature tile mt x all 128 columns of
     // the pair = K-chunk kc = 2*mt + crank, written to chunk buffer kc of BOTH CTAs (rows = that CTA's own columns).
@@ -538,7 +584,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
     auto wait = [&](int id) {
       PPROF_T0();
       if (prof_warp) PTRACE_L0(1 + (int)crank, 0x10 + id);
+#if PNR_IDLE_WAIT
+      mbar_wait_idle(bar(id), (ph >> id) & 1u); ph ^= (1u << id); tc_fence_after();
+#else
       mbar_wait_cluster(bar(id), (ph >> id) & 1u); ph ^= (1u << id); tc_fence_after();
+#endif
       if (prof_warp) PTRACE_L0(1 + (int)crank, 0x40 + id);
       if (prof_warp) PPROF_ADD(id < B_H_FULL ? 9 : 10);
     };
@@ -554,7 +604,7 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-#ifdef PNR_DIAG_NOEPI   // timing diagnostic only (wrong results): no rows were stored, so no bytes are expected
+#if defined(PNR_DIAG_NOEPI) || defined(PNR_DIAG_EPI_NOSTORE)   // timing diagnostic only (wrong results): no rows were stored, so no bytes are expected
           if (crank == 0) mbar_arrive(bar(B_RDY + kc));
           mbar_arrive_cluster_relaxed(land_bar(kc));
 #else
@@ -583,9 +633,14 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       return;
 #endif
       uint32_t v[kNCol / 2], u[kNCol / 2];
+#ifdef PNR_DIAG_EPI_NOALU
+#pragma unroll
+      for (int c = 0; c < kNCol / 2; ++c) { v[c] = 0u; u[c] = 0u; }
+#else
       tmem_ld_nowait<kNCol / 2>(tlane + tcol + peer * kNCol + hs * (kNCol / 2), v);     // both halves in flight at once
       tmem_ld_nowait<kNCol / 2>(tlane + tcol + crank * kNCol + hs * (kNCol / 2), u);
       tmem_ld_wait();
+#endif
       if (prof_warp) PTRACE_L0(1 + (int)crank, 0x80);
       if (c0_busy) wait(B_C0_FREE);
       store_transposed<kNCol / 2, true, true>(rem, v, bias, lane, qd * 32, hs * (kNCol / 2), ASYNC ? land_bar(kc) : 0u);
@@ -713,7 +768,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
       tc_fence_before();
     }
     if (prof && prof_warp && lane == 0) prof[8] += clock64() - t_role0;
+#ifdef PNR_DIAG_OFF_GATHER
+  } else if (false) {
+#else
   } else if (warp == 2 || warp == 3 || warp == 14 || warp == 15) {
+#endif
     // ===================== gather warps: this CTA's 64 columns -> its own z-feature / latent operand rows =======
     const int gw = warp < 4 ? warp - 2 : warp - 12;
     uint32_t par_free = 1;
@@ -827,7 +886,11 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
           {
             PPROF_T0();
             if (gw == 0 && crank == 0) PTRACE_L0(4, 0x10 + B_IN_FREE);
+#if PNR_IDLE_WAIT
+            mbar_wait_idle(bar(B_IN_FREE), par_free);
+#else
             mbar_wait_cluster(bar(B_IN_FREE), par_free);
+#endif
             if (gw == 0 && crank == 0) PTRACE_L0(4, 0x40 + B_IN_FREE);
             if (gw == 0) PPROF_ADD(17);
           }
@@ -947,8 +1010,8 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   long long* prof_dev = nullptr;
   long long* trace_dev = nullptr;
   if (getenv("PNR_TRACE")) {          // event log of pair 0 (takes precedence over the counters)
-    cudaMalloc(&trace_dev, (size_t)5 * pair::kTraceLen * sizeof(long long));
-    cudaMemset(trace_dev, 0, (size_t)5 * pair::kTraceLen * sizeof(long long));
+    cudaMalloc(&trace_dev, (size_t)8 * pair::kTraceLen * sizeof(long long));
+    cudaMemset(trace_dev, 0, (size_t)8 * pair::kTraceLen * sizeof(long long));
     cudaMemcpyToSymbol(pair::g_trace_pair, &trace_dev, sizeof(trace_dev));
     const int ts = getenv("PNR_TRACE_STAGES") ? 1 : 0;
     cudaMemcpyToSymbol(pair::g_trace_stages, &ts, sizeof(ts));
@@ -1009,11 +1072,11 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   if (trace_dev) {
     cudaStreamSynchronize(st);
     long long* null_ptr = nullptr;
-    std::vector<long long> tr((size_t)5 * pair::kTraceLen);
+    std::vector<long long> tr((size_t)8 * pair::kTraceLen);
     cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(getenv("PNR_TRACE"), "a")) {
       fprintf(f, "# launch tiles=%d\n", n_tiles);
-      for (int r = 0; r < 5; ++r)
+      for (int r = 0; r < 8; ++r)
         for (int i = 0; i < pair::kTraceLen && tr[(size_t)r * pair::kTraceLen + i]; ++i)
           fprintf(f, "%d %lld %lld\n", r, tr[(size_t)r * pair::kTraceLen + i] >> 8, tr[(size_t)r * pair::kTraceLen + i] & 0xFF);
       fclose(f);

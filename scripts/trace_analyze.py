@@ -2,7 +2,7 @@
 import sys
 from collections import defaultdict
 
-NAMES = {0: "W_FULL", 5: "W_EMPTY", 10: "IN_READY", 11: "IN_FREE", 12: "X_FULL0", 13: "X_FULL1", 14: "H_FULL0", 15: "H_FULL1",
+NAMES = {0: "W_FULL", 5: "W_EMPTY0", 6: "W_EMPTY1", 7: "W_EMPTY2", 8: "W_EMPTY3", 9: "W_EMPTY4", 10: "IN_READY", 11: "IN_FREE", 12: "X_FULL0", 13: "X_FULL1", 14: "H_FULL0", 15: "H_FULL1",
          16: "RDY0", 17: "RDY1", 18: "RDY2", 19: "RDY3", 20: "X_FREE0", 21: "X_FREE1", 22: "LAND0", 23: "LAND1", 24: "OUT_FREE", 25: "C0_FREE"}
 
 
@@ -14,7 +14,7 @@ def tagname(t):
     if 0x40 <= t < 0x70:
         return "wait< " + NAMES.get(t - 0x40, str(t - 0x40))
     return {0x70: "fenced", 0x71: "stage issued", 0x72: "weights ok", 0x80: "tmem read", 0x81: "remote stored", 0x82: "local stored",
-            0x83: "published", 0xFF: "start"}.get(t, hex(t))
+            0x83: "published", 0x84: "tma issued", 0xFF: "start"}.get(t, hex(t))
 
 
 launches = []
@@ -35,7 +35,7 @@ ev.sort()
 t0 = ev[0][0]
 lo = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 hi = int(sys.argv[4]) if len(sys.argv) > 4 else 60000
-role = {0: "MMA ", 1: "epi0", 2: "epi1", 3: "rely", 4: "gath"}
+role = {0: "MMA ", 1: "epi0", 2: "epi1", 3: "rely", 4: "gath", 5: "prd0", 6: "prd1", 7: "prd2"}
 skip_stage = "--stages" not in sys.argv
 for c, r, t in ev:
     if lo <= c - t0 <= hi:
