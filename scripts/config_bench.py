@@ -17,7 +17,8 @@ import helpers as H  # noqa: E402
 import pixel_nerf_yolo_b200.synth as synth  # noqa: E402
 from pixel_nerf_yolo_b200.render import NeRFRenderer  # noqa: E402
 
-dev = torch.device("cuda", 0)
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+torch.cuda.set_device(dev)
 
 
 def timed(fn, reps=3, warm=1):
@@ -111,6 +112,49 @@ def config5():
                               "rays_per_s": round(n / (ms * 1e-3)), "algorithmic_TFLOPs": round(fl / (ms * 1e-3) / 1e12, 1)}))
 
 
+def config5_sweep_views():
+    """BASELINE config 5 as stated: 24 target views (eval_real.py's turntable, theta = linspace(-180, 180, 25)[:-1], phi 0) of
+    128 x 128 rays = 393 216 rays per (n_coarse, source views) cell.  Under torchrun every rank renders views rank::world (the
+    reference's loop over views, sharded; no data-path collective); time = max over ranks (device events, barrier on both sides)."""
+    import numpy as np
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    thetas = np.linspace(-180, 180, 25)[:-1]
+    mine = [float(t) for t in thetas[rank::world]]
+    for kc in (64, 128, 256):
+        for ns in (1, 3, 5):
+            scene = H.make_scene_dict(num_objs=1, num_views=ns, feat=64, size=128, C=512)
+            net = H.build_net(scene, precision="bf16")
+            r = NeRFRenderer(kc, 32, 16, white_bkgd=True).eval().to(dev)
+            views = [synth.target_rays(128, theta=t, phi=0.0).contiguous().to(dev) for t in mine]
+
+            def go():
+                with torch.no_grad():
+                    for v in views:
+                        r(net, v)
+            go()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); go(); e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            n = 24 * 128 * 128
+            if rank == 0:
+                print(json.dumps({"config": 5, "workload": "24 turntable views x 128x128", "n_gpus": world, "n_coarse": kc, "source_views": ns,
+                                  "rays": n, "ms": round(ms, 2), "rays_per_s": round(n / (ms * 1e-3)),
+                                  "algorithmic_TFLOPs": round(flop_per_ray(ns, 512, kc, 32) * n / (ms * 1e-3) / 1e12, 1)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def yolo():
     """conf/exp/yolo.conf shape: YoloRenderer, 128 samples per ray, 3 anchors x 7 values, 3 x 1792 x 80 x 80 maps (synthetic), 640x640 image."""
     import copy
@@ -139,9 +183,9 @@ def yolo():
                       "algorithmic_TFLOPs": round(per_pt * 128 * rays.shape[0] / (ms * 1e-3) / 1e12, 1)}))
 
 
-which = [a if a == "yolo" else int(a) for a in sys.argv[1:]] or [3, 4, 5, "yolo"]
+which = [a if a in ("yolo", "5views") else int(a) for a in sys.argv[1:]] or [3, 4, 5, "yolo"]
 for w in which:
-    {3: config3, 4: config4, 5: config5, "yolo": yolo}[w]()
+    {3: config3, 4: config4, 5: config5, "yolo": yolo, "5views": config5_sweep_views}[w]()
     if w == 3:
         config3("tf32")
         config3("bf16")
