@@ -35,7 +35,7 @@ EXPORTS = [
     "pnr_render_workspace_bytes", "pnr_render_forward",
 ]
 # lab equipment (csrc/pnr_lab.h, internal): micro-benchmarks and the tcgen05 self test; not part of the product ABI
-LAB_EXPORTS = ["pnr_umma_selftest", "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_umma2_bench", "pnr_dsmem_bench",
+LAB_EXPORTS = ["pnr_umma_selftest", "pnr_ingest_bench", "pnr_ingest_bench_tma", "pnr_umma_bench", "pnr_umma2_bench", "pnr_tma_latency_bench", "pnr_dsmem_bench",
                "pnr_lab_gemm_workspace_bytes", "pnr_lab_rowgemm", "pnr_lab_wgrad"]
 ABI_VERSION = 3
 
@@ -148,6 +148,7 @@ def load() -> C.CDLL:
     lib.pnr_ingest_bench_tma.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp]
     lib.pnr_umma_bench.argtypes = [i32, i32, i32, i32, i32, vp, i32, vp]
     lib.pnr_umma2_bench.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.pnr_tma_latency_bench.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     lib.pnr_dsmem_bench.argtypes = [i32, i32, i32, i32, vp, vp]
     lib.pnr_lab_gemm_workspace_bytes.argtypes = [C.c_longlong, i32, i32]
     lib.pnr_lab_gemm_workspace_bytes.restype = C.c_size_t

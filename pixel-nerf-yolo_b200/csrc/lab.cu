@@ -238,6 +238,95 @@ extern "C" int pnr_ingest_bench_tma(const void* src, int src_stages, int n_stage
   return PNR_OK;
 }
 
+// ---- micro-benchmark 2b: latency of the weight stream's loads (design aid) -----------------------------------------
+// Cluster of 2; per iteration both CTAs synchronise, thread 0 of each issues `k` 16 KiB loads back to back and the time from the
+// first issue to the last completion is accumulated.  mode 0: 1-D bulk copy, own barrier; 1: 2-D tensor-map box (64 x 128 bf16,
+// SWIZZLE_128B), own barrier; 2: the field kernel's form -- cta_group::2 tensor-map loads of BOTH CTAs completing on the LEADER's
+// barrier (32 KiB expected per slot), timed by the leader.  out[pair * 2 + rank] = cycles summed over the iterations.
+namespace pnr {
+__global__ void __launch_bounds__(64, 1)
+tma_latency_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ src, int src_stages, int iters, int mode, int k,
+                   long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t bars = sbase + 8 * kStageBytes;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(bars + 8 * i, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  long long acc = 0;
+  uint32_t par = 0;
+  const int pair = blockIdx.x >> 1;
+  for (int it = 0; it < iters; ++it) {
+    cluster_sync_all();
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int j = 0; j < k; ++j) {
+        const int st = (pair * 131 + it * k + j) % src_stages;
+        const uint32_t dst = sbase + j * kStageBytes, b = bars + 8 * j;
+        if (mode == 0) {
+          mbar_arrive_expect_tx(b, kStageBytes);
+          bulk_g2s(dst, src + (size_t)st * kStageBytes, kStageBytes, b);
+        } else if (mode == 1) {
+          mbar_arrive_expect_tx(b, kStageBytes);
+          tma_load_2d(dst, &tmap, 0, st * kStageRows, b);
+        } else {
+          if (crank == 0) mbar_arrive_expect_tx(b, 2 * kStageBytes);
+          tma_load_2d_2sm(dst, &tmap, 0, ((st & ~1) + (int)crank) * kStageRows, b);
+        }
+      }
+      if (mode != 2 || crank == 0) {
+        for (int j = 0; j < k; ++j) mbar_wait(bars + 8 * j, par);
+        acc += clock64() - t0;
+      }
+    }
+    par ^= 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
+  cluster_sync_all();
+}
+}  // namespace pnr
+
+extern "C" int pnr_tma_latency_bench(const void* src, int src_stages, int iters, int mode, int k, int pairs, long long* out, void* stream) {
+  using namespace pnr;
+  reset_launch_count();
+  PNR_REQUIRE(src && out && iters > 0 && mode >= 0 && mode <= 2 && k >= 1 && k <= 8 && pairs >= 1 && src_stages >= 2, PNR_ERR_ARG,
+              "pnr_tma_latency_bench: bad arguments");
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  PNR_REQUIRE(e == cudaSuccess && fn, PNR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  CUtensorMap tmap;
+  cuuint64_t gdim[2] = {64, (cuuint64_t)src_stages * 128};
+  cuuint64_t gstride[1] = {128};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((EncodeFn)fn)(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)src, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PNR_REQUIRE(r == CUDA_SUCCESS, PNR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  const int smem = 8 * kStageBytes + 256;
+  e = cudaFuncSetAttribute(tma_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(pairs * 2); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, tma_latency_kernel, tmap, (const uint8_t*)src, src_stages, iters, mode, k, out);
+  PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "tma_latency launch: %s", cudaGetErrorString(e));
+  PNR_CHECK_LAUNCH("tma_latency_kernel");
+  return PNR_OK;
+}
+
 // ---- micro-benchmark 3: tcgen05.mma issue/execute cost vs shape (design aid) ---------------------------------
 namespace pnr {
 __global__ void __launch_bounds__(128, 1)

@@ -308,7 +308,7 @@ __device__ __forceinline__ void store_transposed(uint32_t base, const uint32_t* 
 // [12] wait ah_free | [16] gather total [17] wait in_free    (leader CTA's MMA warp; warp 4 and warp 2 of every CTA)
 __device__ long long* g_prof_pair = nullptr;
 // optional event log of CTA pair 0 (PNR_TRACE=<file>, PROF instantiation only): role r writes (clock64 << 8 | tag) entries to
-// g_trace_pair[r * kTraceLen + n].  Roles: 0 MMA thread, 1 / 2 epilogue warp 4 of CTA 0 / 1, 3 relay, 4 gather warp 2 of CTA 0, 5..7 weight producers of CTA 0
+// g_trace_pair[r * kTraceLen + n].  Roles: 0 MMA thread, 1 / 2 epilogue warp 4 of CTA 0 / 1, 3 relay, 4 gather warp 2 of CTA 0, 5..7 / 8..10 weight producers of CTA 0 / CTA 1
 // (0x84 = TMA issued).
 // Tags: 0x10+id wait for barrier id begins, 0x40+id wait satisfied, 0x01..0x04 commit of X_FULL[0], X_FULL[1], H_FULL[0], H_FULL[1]
 // issued, 0x80 TMEM read done, 0x81 remote half stored, 0x82 local half stored, 0x83 published, 0xFF cluster start (clock alignment)
@@ -411,20 +411,20 @@ field_pair_kernel(const pnr_scene sc, const pnr_points q, const __grid_constant_
 #ifdef PNR_DIAG_OFF_RING   // timing diagnostic only (wrong results): no weight ring at all
           continue;
 #endif
-          if (crank == 0) PTRACE(5 + pid, 0x10 + B_W_EMPTY + slot);
+          PTRACE(5 + pid + 3 * (int)crank, 0x10 + B_W_EMPTY + slot);
 #if PNR_IDLE_WAIT
           mbar_wait_idle(bar(B_W_EMPTY + slot), par);
 #else
           mbar_wait_cluster(bar(B_W_EMPTY + slot), par);
 #endif
-          if (crank == 0) PTRACE(5 + pid, 0x40 + B_W_EMPTY + slot);
+          PTRACE(5 + pid + 3 * (int)crank, 0x40 + B_W_EMPTY + slot);
 #ifdef PNR_DIAG_NOWEIGHTS   // timing diagnostic only (wrong results): the weight slot is declared full without loading anything
           if (crank == 0) mbar_arrive(bar(B_W_FULL + slot));
 #else
           if (crank == 0) mbar_arrive_expect_tx(bar(B_W_FULL + slot), 2 * kStageBytes);
           tma_load_2d_2sm(sbase + Smem::w + slot * kStageBytes, &wmap, 0, (st * 2 + (int)crank) * kStageRows, bar(B_W_FULL + slot));
 #endif
-          if (crank == 0) PTRACE(5 + pid, 0x84);
+          PTRACE(5 + pid + 3 * (int)crank, 0x84);
           slot += kProducers;
           if (slot >= kStages) { slot -= kStages; par ^= 1; }
           // next stage id without a division: inside the pre passes the id wraps at s_pre, after them it just continues
@@ -1010,8 +1010,8 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   long long* prof_dev = nullptr;
   long long* trace_dev = nullptr;
   if (getenv("PNR_TRACE")) {          // event log of pair 0 (takes precedence over the counters)
-    cudaMalloc(&trace_dev, (size_t)8 * pair::kTraceLen * sizeof(long long));
-    cudaMemset(trace_dev, 0, (size_t)8 * pair::kTraceLen * sizeof(long long));
+    cudaMalloc(&trace_dev, (size_t)11 * pair::kTraceLen * sizeof(long long));
+    cudaMemset(trace_dev, 0, (size_t)11 * pair::kTraceLen * sizeof(long long));
     cudaMemcpyToSymbol(pair::g_trace_pair, &trace_dev, sizeof(trace_dev));
     const int ts = getenv("PNR_TRACE_STAGES") ? 1 : 0;
     cudaMemcpyToSymbol(pair::g_trace_stages, &ts, sizeof(ts));
@@ -1072,11 +1072,11 @@ int field_forward_pair(const pnr_scene* sc, const pnr_points* q, const pnr_mlp_p
   if (trace_dev) {
     cudaStreamSynchronize(st);
     long long* null_ptr = nullptr;
-    std::vector<long long> tr((size_t)8 * pair::kTraceLen);
+    std::vector<long long> tr((size_t)11 * pair::kTraceLen);
     cudaMemcpy(tr.data(), trace_dev, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(getenv("PNR_TRACE"), "a")) {
       fprintf(f, "# launch tiles=%d\n", n_tiles);
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < 11; ++r)
         for (int i = 0; i < pair::kTraceLen && tr[(size_t)r * pair::kTraceLen + i]; ++i)
           fprintf(f, "%d %lld %lld\n", r, tr[(size_t)r * pair::kTraceLen + i] >> 8, tr[(size_t)r * pair::kTraceLen + i] & 0xFF);
       fclose(f);

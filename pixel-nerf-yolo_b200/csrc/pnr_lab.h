@@ -17,6 +17,9 @@ int pnr_ingest_bench(const void* src, int src_stages, int n_stages, int depth, i
 /* same through a 2-D tensor map (cp.async.bulk.tensor.2d), box = 64 x box_rows bf16, optional 128B swizzle. */
 int pnr_ingest_bench_tma(const void* src, int src_stages, int n_stages, int depth, int grid, long long* out,
                          int box_rows, int swizzle, void* stream);
+/* latency of k 16 KiB loads issued back to back per CTA of a cluster of 2 (mode 0 bulk 1-D, 1 tensor-map box, 2 the field kernel's
+ * cta_group::2 form completing on the leader's barrier); out[2 * pairs] = cycles summed over iters. */
+int pnr_tma_latency_bench(const void* src, int src_stages, int iters, int mode, int k, int pairs, long long* out, void* stream);
 /* cycles for `iters` x 8 tcgen05.mma (kind::f16, bf16, K=16) of shape M x N issued back to back from shared-memory operands. */
 int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid, long long* out, int commit_every, void* stream);
 /* the CTA-pair MMA (cta_group::2, M = 256, N) in isolation: out[pairs] = cycles for iters x 8 MMAs; bg bit 0 = concurrent 16 KiB

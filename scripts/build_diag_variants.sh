@@ -30,6 +30,7 @@ if [ -n "$ONLY" ]; then
       idle3) build_one idle3 -DPNR_IDLE_WAIT=3 & ;;
       epi_nostore) build_one epi_nostore -DPNR_DIAG_EPI_NOSTORE & ;;
       epi_noalu) build_one epi_noalu -DPNR_DIAG_EPI_NOALU & ;;
+      ring_gather) build_one ring_gather -DPNR_DIAG_OFF_WAITS -DPNR_DIAG_OFF_EPI & ;;
       nogather) build_one nogather -DPNR_DIAG_NOGATHER & ;;
       *) echo "unknown variant $v" ;;
     esac

@@ -30,12 +30,12 @@ print("clock offset CTA1 - CTA0 at start:", off)
 ev = []
 for r, lst in L.items():
     for c, t in lst:
-        ev.append((c - (off if r in (2, 3) else 0), r, t))
+        ev.append((c - (off if r in (2, 3, 8, 9, 10) else 0), r, t))
 ev.sort()
 t0 = ev[0][0]
 lo = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 hi = int(sys.argv[4]) if len(sys.argv) > 4 else 60000
-role = {0: "MMA ", 1: "epi0", 2: "epi1", 3: "rely", 4: "gath", 5: "prd0", 6: "prd1", 7: "prd2"}
+role = {0: "MMA ", 1: "epi0", 2: "epi1", 3: "rely", 4: "gath", 5: "prd0", 6: "prd1", 7: "prd2", 8: "PRD0", 9: "PRD1", 10: "PRD2"}
 skip_stage = "--stages" not in sys.argv
 for c, r, t in ev:
     if lo <= c - t0 <= hi:
