@@ -398,7 +398,8 @@ extern "C" int pnr_umma_bench(int M, int N, int iters, int a_stride_kb, int grid
 // Leader thread issues iters x 8 MMAs (two groups of 4 = two "stages": A from a ring of 16 KiB slots, B from 8 KiB k-blocks), a
 // multicast commit after each group when commit_every == 4.  bg: bit 0 = warps 2, 3 of each CTA stream 16 KiB bulk copies from
 // global memory into a 4-slot ring (the weight stream's shared-memory writes), bit 1 = warps 4..7 keep writing 16-byte
-// st.shared rows (the epilogue / gather stores).  out[pair] = cycles of the MMA loop.
+// st.shared rows (the epilogue / gather stores).  out[pair] = cycles of the MMA loop; out[pairs + 4 * cta + w] = 8 KiB bulk copies
+// loader warp w of that CTA completed meanwhile (bg bit 0; bit 2 = no MMAs at all, the loaders' baseline).
 namespace pnr {
 __global__ void __launch_bounds__(256, 1)
 umma2_bench_kernel(int N, int iters, int commit_every, int a_slots, int bg, const uint8_t* __restrict__ src, long long* __restrict__ out) {
@@ -410,7 +411,7 @@ umma2_bench_kernel(int N, int iters, int commit_every, int a_slots, int bg, cons
   const uint32_t bar0 = sbase + kBar;
   volatile int* done = reinterpret_cast<volatile int*>(smem + kBar + 256);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 12; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 12; ++i) mbar_init(bar0 + 8 * i, 1);   // 0, 1: MMA; 2..9: loader slots
     *done = 0;
     fence_barrier_init();
   }
@@ -429,6 +430,9 @@ umma2_bench_kernel(int N, int iters, int commit_every, int a_slots, int bg, cons
       if (elect_one()) {
         t0 = clock64();
         int slot = 0;
+        if (bg & 4) {                                    // baseline for the background traffic: no MMAs, same duration
+          while (clock64() - t0 < (long long)iters * 8 * (N / 2)) {}
+        } else
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -450,23 +454,30 @@ umma2_bench_kernel(int N, int iters, int commit_every, int a_slots, int bg, cons
         asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa_u32(sbase + kBar + 256, 1)), "r"(1) : "memory");
       }
     }
-  } else if ((bg & 1) && (warp == 2 || warp == 3)) {
+  } else if ((bg & 1) && (warp == 2 || warp == 3 || warp == 6 || warp == 7)) {
+    // four loader warps, each keeps two 8 KiB bulk copies in flight all the time (64 KiB in flight per CTA)
     if (elect_one()) {
-      const int w = warp - 2;
+      const int w = warp < 4 ? warp - 2 : warp - 4;        // 0..3
       uint32_t par[2] = {0, 0};
-      const uint8_t* s0 = src + ((size_t)blockIdx.x * 2 + w) * (64 * 16384);
-      int i = 0;
-      for (; !*done; ++i) {
+      const uint8_t* s0 = src + (size_t)w * (32 * 16384);      // every CTA streams the same 2 MiB: L2 hits, like the weight stream
+      long long n = 0;
+      for (int sl = 0; sl < 2; ++sl) {
+        const uint32_t b = bar0 + 8 * (2 + w * 2 + sl);
+        mbar_arrive_expect_tx(b, 8192);
+        bulk_g2s(sbase + kBg + (w * 2 + sl) * 8192, s0 + (size_t)sl * 8192, 8192, b);
+      }
+      for (int i = 2; !*done; ++i) {
         const int sl = i & 1;
         const uint32_t b = bar0 + 8 * (2 + w * 2 + sl);
-        mbar_arrive_expect_tx(b, 16384);
-        bulk_g2s(sbase + kBg + (w * 2 + sl) * 16384, s0 + (size_t)(i & 63) * 16384, 16384, b);
-        if (i >= 1) { const int ps = (i - 1) & 1; mbar_wait(bar0 + 8 * (2 + w * 2 + ps), par[ps]); par[ps] ^= 1; }
+        mbar_wait(b, par[sl]); par[sl] ^= 1; ++n;
+        mbar_arrive_expect_tx(b, 8192);
+        bulk_g2s(sbase + kBg + (w * 2 + sl) * 8192, s0 + (size_t)(i & 63) * 8192, 8192, b);
       }
-      if (i >= 1) { const int ps = (i - 1) & 1; mbar_wait(bar0 + 8 * (2 + w * 2 + ps), par[ps]); }   // the last copy has landed
+      for (int sl = 0; sl < 2; ++sl) mbar_wait(bar0 + 8 * (2 + w * 2 + sl), par[sl]);      // the last copies have landed
+      out[(gridDim.x >> 1) + blockIdx.x * 4 + w] = n;      // 8 KiB copies completed while the MMAs ran
     }
     __syncwarp();
-  } else if ((bg & 2) && warp >= 4) {
+  } else if ((bg & 2) && (warp == 4 || warp == 5)) {
     uint32_t a = sbase + kSt + ((warp - 4) * 32 + lane) * 16;
     while (!*done) {
 #pragma unroll
@@ -486,7 +497,7 @@ extern "C" int pnr_umma2_bench(int N, int iters, int commit_every, int a_slots, 
   reset_launch_count();
   PNR_REQUIRE(out && N >= 32 && N <= 256 && N % 32 == 0 && iters > 0 && a_slots >= 1 && a_slots <= 6 && pairs >= 1, PNR_ERR_ARG,
               "pnr_umma2_bench: bad arguments");
-  PNR_REQUIRE(!(bg & 1) || src, PNR_ERR_ARG, "pnr_umma2_bench: bg bit 0 needs a source buffer of pairs * 4 * 1 MiB");
+  PNR_REQUIRE(!(bg & 1) || src, PNR_ERR_ARG, "pnr_umma2_bench: bg bit 0 needs a source buffer of pairs * 4 MiB");
   const int smem = 200 * 1024 + 512;
   cudaError_t e = cudaFuncSetAttribute(umma2_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   PNR_REQUIRE(e == cudaSuccess, PNR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));

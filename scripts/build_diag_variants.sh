@@ -31,6 +31,8 @@ if [ -n "$ONLY" ]; then
       epi_nostore) build_one epi_nostore -DPNR_DIAG_EPI_NOSTORE & ;;
       epi_noalu) build_one epi_noalu -DPNR_DIAG_EPI_NOALU & ;;
       ring_gather) build_one ring_gather -DPNR_DIAG_OFF_WAITS -DPNR_DIAG_OFF_EPI & ;;
+      stages4) build_one stages4 -DPNR_STAGES=4 & ;;
+      stages3) build_one stages3 -DPNR_STAGES=3 & ;;
       nogather) build_one nogather -DPNR_DIAG_NOGATHER & ;;
       *) echo "unknown variant $v" ;;
     esac

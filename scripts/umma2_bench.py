@@ -10,12 +10,15 @@ iters = 4000
 pairs = 74
 src = torch.zeros(pairs * 4 << 20, dtype=torch.uint8, device=dev)
 for N in (64, 128, 256):
-    for commit_every in (0, 4):
-        for a_slots in (1, 5):
-            for bg in (0, 1, 2, 3):
-                out = torch.zeros(pairs, dtype=torch.int64, device=dev)
+    for commit_every in (4,):
+        for a_slots in (5,):
+            for bg in (0, 1, 5, 3, 7):
+                out = torch.zeros(pairs * 10, dtype=torch.int64, device=dev)
                 for rep in range(2):
                     _lib.check(lib.pnr_umma2_bench(N, iters, commit_every, a_slots, bg, pairs, src.data_ptr(), out.data_ptr(), _lib.stream_ptr(dev)), "umma2_bench")
                     torch.cuda.synchronize()
-                cyc = out.float().mean().item() / (iters * 8)
-                print(f"N={N:3d} commit_every={commit_every} a_slots={a_slots} bg={bg}  cycles/MMA={cyc:7.1f}  MAC/clk/SM={128 * N * 16 / cyc:7.0f}  ({100 * 128 * N * 16 / cyc / 4096:5.1f} % of 4096)", flush=True)
+                total = out[:pairs].float().mean().item()
+                cyc = total / (iters * 8)
+                copies = out[pairs:pairs + pairs * 8].float().reshape(pairs * 2, 4).sum(1).mean().item()      # per CTA (four loader warps)
+                print(f"N={N:3d} commit_every={commit_every} a_slots={a_slots} bg={bg}  cycles/MMA={cyc:7.1f}  MAC/clk/SM={128 * N * 16 / cyc:7.0f}  ({100 * 128 * N * 16 / cyc / 4096:5.1f} % of 4096)"
+                      + (f"  concurrent bulk copies into smem: {copies * 8192 / total:6.1f} B/clk/SM" if bg & 1 else "") + ("   [no MMAs issued: baseline of the background traffic]" if bg & 4 else ""), flush=True)
